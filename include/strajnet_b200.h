@@ -1,0 +1,235 @@
+/*
+ * strajnet_b200 -- C ABI of the B200-native occupancy-flow forward path.
+ *
+ * This is the drop-in boundary.  The reference (georgeliu233/STrajNet) has no
+ * FFI of its own: its hot path sits behind the Keras Layer/Model call protocol
+ * (`__init__ / build() / call()`), so every entry point below replaces one Keras `call()`
+ * and cites it as  <file>:<line>  relative to the reference tree.  The Python mirror of
+ * those classes (strajnet_b200/layers.py, swinT.py) binds these symbols through ctypes;
+ * INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every data pointer is a DEVICE pointer unless the name ends in `_host`;
+ *     weight STRUCTS live in host memory and hold device pointers;
+ *   - tensors are channels-last, row-major, contiguous, 16-byte aligned;
+ *   - `dtype` selects the activation type of `x`/`y`/intermediates (SJ_F32 or SJ_BF16);
+ *     model inputs (rasters, actors) are always fp32; weights are fp32 ([in,out] Keras layout)
+ *     with an optional bf16 tensor-core copy (`w_tc`, [out,in] K-major) used when dtype==SJ_BF16;
+ *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state;
+ *     the caller owns all buffers including `workspace`; safe to capture in a CUDA graph;
+ *   - return 0 (SJ_OK) or a negative SjStatus; never throws.
+ */
+#ifndef STRAJNET_B200_H_
+#define STRAJNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sj_stream_t; /* cudaStream_t */
+
+typedef enum { SJ_F32 = 0, SJ_BF16 = 1 } SjDType;
+
+typedef enum {
+  SJ_OK = 0,
+  SJ_EINVAL = -1,       /* bad shape / null pointer / misalignment              */
+  SJ_EUNSUPPORTED = -2, /* configuration outside what the kernels implement     */
+  SJ_ECUDA = -3,        /* a CUDA call failed (see sj_last_cuda_error)          */
+  SJ_EWORKSPACE = -4    /* workspace too small (see the *_workspace_bytes call) */
+} SjStatus;
+
+/* Dense / conv weights.  w: fp32 [K,N] (Keras [in,out], conv taps flattened into K);
+ * b: fp32 [N] or NULL; w_tc: bf16 [N,K] (K-major) tensor-core copy or NULL.          */
+typedef struct { const float* w; const float* b; const void* w_tc; } SjLinear;
+typedef struct { const float* g; const float* b; } SjNorm; /* LayerNormalization gamma/beta */
+
+/* SwinTransformerBlock (modules.py:163-262) incl. WindowAttention (:66-134) and Mlp (:31-46). */
+typedef struct {
+  SjNorm norm1;
+  SjLinear qkv;           /* [C,3C] + [3C]            modules.py:76  */
+  const float* rpb_table; /* [(2ws-1)^2, heads]       modules.py:83  */
+  SjLinear proj;          /* [C,C] + [C]              modules.py:79  */
+  SjNorm norm2;
+  SjLinear fc1;           /* [C,4C] + [4C]            modules.py:36  */
+  SjLinear fc2;           /* [4C,C] + [C]             modules.py:37  */
+} SjSwinBlockW;
+
+typedef struct { SjNorm norm; SjLinear reduction; } SjPatchMergeW; /* modules.py:265-292: LN(4C), [4C,2C] no bias */
+typedef struct { SjLinear proj; SjNorm norm; } SjPatchEmbedW;      /* modules.py:417-446: [16*Cin,E]+[E], LN(E) */
+
+/* BasicLayer (modules.py:317-364) */
+typedef struct {
+  const SjSwinBlockW* blocks_host; /* host array of `depth` blocks */
+  int depth, dim, heads, has_down;
+  SjPatchMergeW down;
+} SjBasicLayerW;
+
+/* SwinTransformerEncoder as configured by STrajNet (modules.py:782-785; forward :570-624) */
+typedef struct {
+  SjPatchEmbedW pe_vec, pe_map, pe_flow;
+  SjNorm flow_norm, all_patch_norm;
+  SjBasicLayerW flow_layer;
+  SjBasicLayerW layers[4];
+  int num_layers, window_size, embed_dim;
+} SjEncoderW;
+
+/* FGMSA (FG_MSA.py:20-183), n_heads = n_groups = 8, 48 channels per head, 16x16 tokens */
+typedef struct {
+  SjLinear qkv;            /* proj_q|proj_k|proj_v concatenated: [384,1152] + [1152]  FG_MSA.py:58-62 */
+  const float* conv0_w;    /* [3,3,48,384]  grouped 3x3, groups=8                      FG_MSA.py:51    */
+  const float* conv0_b;    /* [384] */
+  SjNorm conv_norm;        /* eps 1e-3                                                FG_MSA.py:52    */
+  const float* offproj_w;  /* [48,2] no bias                                          FG_MSA.py:54    */
+  const float* offproj2_w; /* [2,384] (fg only, else NULL)                            FG_MSA.py:56    */
+  const float* offproj2_b; /* [384] */
+  const float* rpe_table;  /* [31,31,8]                                               FG_MSA.py:70    */
+  SjLinear out;            /* proj_out [384,384] + [384]                              FG_MSA.py:64    */
+} SjFgmsaW;
+
+/* TrajNetCrossAttention (trajNet.py:236-319) = TrajNet (:91-187) + 8x Cross_AttentionT (:189-234).
+ * tfa.layers.MultiHeadAttention kernels [H,in,hs] are re-laid-out as [in, H*hs] (heads concatenated
+ * along columns); head_size 42 is kept at 42 with the 126 columns zero-padded to 128.              */
+typedef struct {
+  const float* node_w;  /* [5,64]   Conv1D(64,1) kernel    trajNet.py:32 */
+  const float* node_b;  /* [64] */
+  SjLinear node_qkv;    /* [64,768] = q(4x64)|k|v, no bias trajNet.py:33 */
+  SjLinear node_proj;   /* [256,320] + [320] */
+  const float* vec_w;   /* [3,64] no bias                  trajNet.py:35 */
+  SjLinear sublayer;    /* [384,384] + [384], ELU          trajNet.py:36 */
+  SjLinear ia_q;        /* interaction Cross_Attention (trajNet.py:65-87): [384,384] */
+  SjLinear ia_kv;       /* [384,768] = k|v */
+  SjLinear ia_proj;     /* [384,384] + [384] */
+  SjNorm ia_norm1;
+  SjLinear ia_ffn1;     /* [384,1536] + b, ELU */
+  SjLinear ia_ffn2;     /* [1536,384] + b */
+  SjNorm ia_norm2;
+  SjNorm obs_norm, occ_norm;
+  const float* seg_w;   /* [2,384] */
+  /* the 8 per-waypoint Cross_AttentionT, stacked on a leading dim of 8 */
+  SjLinear ca_q;        /* [8][384,128]  (3 heads x 42 = 126 cols, padded) */
+  SjLinear ca_kv;       /* [8][384,256]  k at cols 0..125, v at cols 128..253 */
+  SjLinear ca_proj;     /* [8][128,128] + [8][128] (rows 126,127 zero) */
+  SjNorm ca_norm1;      /* [8][128] */
+  SjLinear ca_ffn1;     /* [8][128,512] + [8][512], ELU */
+  SjLinear ca_ffn2;     /* [8][512,384] + [8][384] */
+  SjNorm ca_norm2;      /* [8][384] */
+} SjTrajW;
+
+/* Pyramid3DDecoder as configured by STrajNet (modules.py:800-801; forward :739-772).
+ * 3x3 kernels are flattened to [9*Cin, Cout] (tap-major).  The (8,1,1) Conv3D over the
+ * 8x-repeated skip tensor is pre-collapsed on the host to 8 per-waypoint 1x1 kernels
+ * W_eff[t] = sum_{k: 0<=t+k-3<=7} W[k]  (TF SAME: 3 before / 4 after), stored [8][Cin,Cout].
+ * For dtype==SJ_BF16, upconv*.w_tc holds the sub-pixel-folded kernels: nearest-x2 followed by a
+ * 3x3 SAME conv equals four 2x2 convs on the low-res input; layout [4 phases][Cout][4*Cin] bf16. */
+typedef struct {
+  SjLinear upconv[4];   /* 384->192, 192->128, 128->96, 96->48, ELU */
+  SjLinear res[2];      /* collapsed res_layer: [8][192,192], [8][96,128], ELU */
+  SjLinear res_f;       /* collapsed res_f: [8][96,128], ELU */
+  SjLinear upconv_f[2]; /* 128->96, 96->48, ELU */
+  const float* out_w;   /* [2][9*48,2]: output_layer then output_layer_f */
+  const float* out_b;   /* [2][2] */
+} SjDecoderW;
+
+typedef struct {
+  SjEncoderW encoder;
+  SjFgmsaW fgmsa;
+  SjTrajW traj;
+  SjDecoderW decoder;
+  int fg_msa, fg, large_ogm; /* STrajNet ctor flags, modules.py:778-779 */
+} SjModelW;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int sj_version(void);
+/* sizeof() of the weight structs, in declaration order (SjLinear=0 ... SjModelW=10): lets a foreign-language
+ * binding verify its struct layout against the library it loaded */
+size_t sj_sizeof(int which);
+const char* sj_strerror(int status);
+const char* sj_last_cuda_error(void); /* text of the last CUDA failure seen by this thread */
+/* number of kernels launched by this thread through the library since the last reset */
+long long sj_launch_count(int reset);
+
+/* ---- integer maps (bit-exact rows of SURVEY §8 a3/a4/a5) --------------------------------- */
+/* WindowAttention.build, modules.py:88-100: int64 [ws*ws, ws*ws] */
+int sj_relative_position_index(int ws, int64_t* out, sj_stream_t stream);
+/* SwinTransformerBlock.build, modules.py:189-214: float [nW, ws*ws, ws*ws] in {0,-100} */
+int sj_shift_attn_mask(int H, int W, int ws, int shift, float* out, sj_stream_t stream);
+/* roll(-shift) + window_partition as a gather map: out[w*ws*ws+n] = source token index in [0,H*W);
+ * shift=0 gives window_partition alone (modules.py:49-55, :230-239) */
+int sj_window_token_map(int H, int W, int ws, int shift, int32_t* out, sj_stream_t stream);
+/* window_partition / window_reverse on data (modules.py:49-63) */
+int sj_window_partition_fwd(const void* x, void* windows, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream);
+int sj_window_reverse_fwd(const void* windows, void* x, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream);
+
+/* ---- layers ------------------------------------------------------------------------------ */
+/* Mlp.call, modules.py:40-46: y = fc2(Gelu(fc1(x))), x [M,C] */
+size_t sj_mlp_workspace_bytes(int M, int C, int hidden, int dtype);
+int sj_mlp_fwd(const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2, int M, int C, int hidden,
+               int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* WindowAttention.call, modules.py:103-134: xw [B_,N=ws*ws,C]; mask [nW,N,N] fp32 or NULL */
+size_t sj_window_attention_workspace_bytes(int B_, int C, int dtype);
+int sj_window_attention_fwd(const void* xw, void* y, const SjSwinBlockW* w, int B_, int C, int heads, int ws,
+                            const float* mask, int nW, int dtype, void* workspace, size_t workspace_bytes,
+                            sj_stream_t stream);
+
+/* SwinTransformerBlock.call, modules.py:220-262: x,y [B,H*W,C] */
+size_t sj_swin_block_workspace_bytes(int B, int H, int W, int C, int dtype);
+int sj_swin_block_fwd(const void* x, void* y, const SjSwinBlockW* w, int B, int H, int W, int C, int heads,
+                      int ws, int shift, int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* PatchMerging.call, modules.py:274-292: x [B,H*W,C] -> y [B,H*W/4,2C]; add (same shape as y) or NULL
+ * is added to the result (the `x + flow_x` of modules.py:613) */
+size_t sj_patch_merging_workspace_bytes(int B, int H, int W, int C, int dtype);
+int sj_patch_merging_fwd(const void* x, void* y, const SjPatchMergeW* w, const void* add, int B, int H, int W,
+                         int C, int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* PatchEmbed.call, modules.py:437-446: img fp32 [B,S,S,Cin] with element stride `elem_stride`
+ * between channels (2 selects plane 0 of ogm[...,11,2]) -> y [B,(S/4)^2,E] */
+int sj_patch_embed_fwd(const float* img, void* y, const SjPatchEmbedW* w, int B, int S, int Cin, int elem_stride,
+                       int E, int dtype, sj_stream_t stream);
+
+/* BasicLayer.call, modules.py:351-364: returns (x_down or x, res).  y_down may be NULL when !has_down. */
+size_t sj_basic_layer_workspace_bytes(int B, int H, int W, int C, int dtype);
+int sj_basic_layer_fwd(const void* x, void* y_down, void* res, const SjBasicLayerW* w, int B, int H, int W,
+                       int ws, int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* SwinTransformerEncoder.call, modules.py:626 / :570-624.  ogm fp32 [B,S,S,11,2], map fp32 [B,256,256,3],
+ * flow fp32 [B,S,S,2]; outputs flow_res [B,4096,96], res0 [B,4096,96], res1 [B,1024,192], res2 [B,256,384] */
+size_t sj_encoder_workspace_bytes(int B, int S, int dtype);
+int sj_encoder_fwd(const float* ogm, const float* map_img, const float* flow, void* flow_res, void* res0,
+                   void* res1, void* res2, const SjEncoderW* w, int B, int S, int large_input, int dtype,
+                   void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* FGMSA.call, FG_MSA.py:106-183: x [B,16,16,384] -> y [B,16,16,384], pos fp32 [B,8,16,16,2],
+ * flow_hidden [B,8,16,16,384] (NULL to skip; requires offproj2) */
+size_t sj_fgmsa_workspace_bytes(int B, int dtype);
+int sj_fgmsa_fwd(const void* x, void* y, float* pos, void* flow_hidden, const SjFgmsaW* w, int B, int dtype,
+                 void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* TrajNetCrossAttention.call, trajNet.py:284-319: pic [B,8,256,384], obs fp32 [B,48,11,8],
+ * occ fp32 [B,16,11,8] -> out [B,8,256,384] */
+size_t sj_traj_cross_attention_workspace_bytes(int B, int dtype);
+int sj_traj_cross_attention_fwd(const void* pic, const float* obs, const float* occ, void* out, const SjTrajW* w,
+                                int B, int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
+/* Pyramid3DDecoder.call, modules.py:739-772: x [B,8,16,16,384] + skips -> fp32 out.
+ * out_layout 0: [B,8,256,256,4] (the Keras layer's own result); 1: [B,256,256,32] (STrajNet, modules.py:838) */
+size_t sj_decoder_workspace_bytes(int B, int dtype);
+int sj_decoder_fwd(const void* x, const void* flow_res, const void* res0, const void* res1, float* out,
+                   const SjDecoderW* w, int B, int out_layout, int dtype, void* workspace, size_t workspace_bytes,
+                   sj_stream_t stream);
+
+/* STrajNet.call, modules.py:815-839: -> out fp32 [B,256,256,32] */
+size_t sj_strajnet_workspace_bytes(int B, int S, int dtype);
+int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, const float* obs, const float* occ,
+                    float* out, const SjModelW* w, int B, int S, int dtype, void* workspace, size_t workspace_bytes,
+                    sj_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRAJNET_B200_H_ */

@@ -1,0 +1,682 @@
+// C-ABI entry points (include/strajnet_b200.h) and the host-side sequencing of the forward path.
+// Every *_impl function mirrors one `call()` of the reference (file:line cited in the header).
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace sj {
+
+TlsState& tls() {
+  static thread_local TlsState s;
+  return s;
+}
+
+void note_launch(Ctx& c, const char* what) {
+  tls().launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(tls().cuda_err, sizeof(tls().cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    c.fail(SJ_ECUDA);
+  }
+}
+
+namespace {
+
+inline const void* adv(const Ctx& c, const void* p, long long elems) {
+  return p ? (const char*)p + elems * (long long)c.esize() : nullptr;
+}
+
+// C[M,N] = act(A[M,K] . W + b) (+ R)
+void linear(Ctx& c, const void* A, int lda, const SjLinear& w, void* C, int ldc, int M, int N, int K, int act,
+            const void* R = nullptr, int ldr = 0) {
+  GemmP g;
+  g.A = A; g.lda = lda; g.W = w.w; g.ldw = N; g.bias = w.b; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.R = R; g.ldr = ldr;
+  gemm(c, g);
+}
+
+// ---- SwinTransformerBlock.call (modules.py:220-262) ---------------------------------------------
+void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int B, int H, int W, int C, int heads,
+                     int ws, int shift, const int* map) {
+  if (ws != 8 || H % 8 || W % 8 || H < 8 || W < 8 || C % 16 || heads <= 0 || C % heads) { c.fail(SJ_EUNSUPPORTED); return; }
+  if (H <= ws || W <= ws) shift = 0;  // modules.py:173-175
+  if (shift < 0 || shift >= ws) { c.fail(SJ_EINVAL); return; }
+  const int L = H * W;
+  const long long M = (long long)B * L;
+  size_t mark = c.ws.mark();
+  float* mean = (float*)c.alloc(M * 4);
+  float* rstd = (float*)c.alloc(M * 4);
+  if (!map) {
+    int* m = (int*)c.alloc((size_t)L * 4);
+    window_token_map(c, H, W, ws, shift, m);
+    map = m;
+  }
+  void* qkv = c.alloc_act(M * 3 * C);
+  void* o = c.alloc_act(M * C);
+  void* x1 = c.alloc_act(M * C);
+  void* hbuf = c.alloc_act(M * 4 * C);
+
+  ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
+  {  // norm1 -> roll -> partition -> qkv   (modules.py:226-239, :105)
+    GemmP g;
+    g.A = x; g.lda = C; g.W = w.qkv.w; g.ldw = 3 * C; g.bias = w.qkv.b; g.C = qkv; g.ldc = 3 * C;
+    g.M = (int)M; g.N = 3 * C; g.K = C;
+    g.am.map = map; g.am.map_len = L;
+    g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm1.g; g.ln_b = w.norm1.b;
+    gemm(c, g);
+  }
+  window_attn_core(c, qkv, o, w.rpb_table, (int)(M / 64), C, heads, shift > 0 ? 1 : 0, H, W, shift, nullptr, 0);
+  {  // proj -> window_reverse -> roll back -> + shortcut   (modules.py:132, :245-258)
+    GemmP g;
+    g.A = o; g.lda = C; g.W = w.proj.w; g.ldw = C; g.bias = w.proj.b; g.C = x1; g.ldc = C;
+    g.M = (int)M; g.N = C; g.K = C;
+    g.cm.map = map; g.cm.map_len = L;
+    g.R = x; g.ldr = C;
+    gemm(c, g);
+  }
+  ln_stats(c, x1, (int)M, C, C, 1e-5f, mean, rstd);
+  {  // norm2 -> fc1 -> GELU   (modules.py:260, :41-42)
+    GemmP g;
+    g.A = x1; g.lda = C; g.W = w.fc1.w; g.ldw = 4 * C; g.bias = w.fc1.b; g.C = hbuf; g.ldc = 4 * C;
+    g.M = (int)M; g.N = 4 * C; g.K = C; g.act = ACT_GELU;
+    g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
+    gemm(c, g);
+  }
+  linear(c, hbuf, 4 * C, w.fc2, y, C, (int)M, C, 4 * C, ACT_NONE, x1, C);  // fc2 + residual
+  c.ws.release(mark);
+}
+
+// ---- PatchMerging.call (modules.py:274-292) -----------------------------------------------------
+void patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, const void* add, int B, int H, int W,
+                        int C) {
+  if (H % 2 || W % 2 || C % 16) { c.fail(SJ_EUNSUPPORTED); return; }
+  const int M = B * (H / 2) * (W / 2);
+  size_t mark = c.ws.mark();
+  float* mean = (float*)c.alloc((size_t)M * 4);
+  float* rstd = (float*)c.alloc((size_t)M * 4);
+  ln_stats_merge(c, x, B, H, W, C, 1e-5f, mean, rstd);
+  GemmP g;
+  g.amode = A_MERGE; g.A = x; g.H = H; g.Wd = W; g.Cin = C;
+  g.W = w.reduction.w; g.ldw = 2 * C; g.C = y; g.ldc = 2 * C; g.M = M; g.N = 2 * C; g.K = 4 * C;
+  g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm.g; g.ln_b = w.norm.b;
+  g.R = add; g.ldr = 2 * C;
+  gemm(c, g);
+  c.ws.release(mark);
+}
+
+// ---- BasicLayer.call (modules.py:351-364) -------------------------------------------------------
+void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBasicLayerW& w, const void* add, int B,
+                      int H, int W, int ws) {
+  const int C = w.dim;
+  const long long n = (long long)B * H * W * C;
+  if (w.depth < 1 || !w.blocks_host || !res) { c.fail(SJ_EINVAL); return; }
+  size_t mark = c.ws.mark();
+  void* tmp = w.depth > 1 ? c.alloc_act(n) : nullptr;
+  int* maps[2] = {(int*)c.alloc((size_t)H * W * 4), (int*)c.alloc((size_t)H * W * 4)};
+  const int sh = (H <= ws || W <= ws) ? 0 : ws / 2;
+  window_token_map(c, H, W, ws, 0, maps[0]);
+  window_token_map(c, H, W, ws, sh, maps[1]);
+  const void* cur = x;
+  for (int i = 0; i < w.depth; ++i) {
+    void* dst = ((w.depth - 1 - i) % 2 == 0) ? res : tmp;
+    int shift = (i % 2 == 0) ? 0 : sh;  // modules.py:331-332
+    swin_block_impl(c, cur, dst, w.blocks_host[i], B, H, W, C, w.heads, ws, shift, maps[i % 2]);
+    cur = dst;
+  }
+  if (w.has_down) {
+    if (!y_down) { c.fail(SJ_EINVAL); return; }
+    patch_merging_impl(c, res, y_down, w.down, add, B, H, W, C);
+  }
+  c.ws.release(mark);
+}
+
+// ---- SwinTransformerEncoder.forward_features (modules.py:570-624) -------------------------------
+void encoder_impl(Ctx& c, const float* ogm, const float* map_img, const float* flow, void* flow_res, void* res0,
+                  void* res1, void* res2, const SjEncoderW& w, int B, int S, int large) {
+  if (w.num_layers != 3 || w.window_size != 8 || w.embed_dim != 96) { c.fail(SJ_EUNSUPPORTED); return; }
+  if ((large && S != 512) || (!large && S != 256)) { c.fail(SJ_EUNSUPPORTED); return; }  // Q13
+  const int E = w.embed_dim, P = S / 4;
+  const long long L0 = (long long)P * P;
+  size_t mark = c.ws.mark();
+  void* outs[4] = {flow_res, res0, res1, res2};
+  void* full[4] = {flow_res, res0, res1, res2};
+  if (large) {
+    full[0] = c.alloc_act(B * L0 * E);
+    full[1] = c.alloc_act(B * L0 * E);
+    full[2] = c.alloc_act(B * L0 / 4 * 2 * E);
+    full[3] = c.alloc_act(B * L0 / 16 * 4 * E);
+  }
+  void* f0 = c.alloc_act(B * L0 * E);
+  void* flow_x = c.alloc_act(B * L0 / 4 * 2 * E);
+  {  // patch_embed_flow -> flow_norm (modules.py:576-577)
+    PatchEmbedP p;
+    p.img[0] = flow; p.Cin[0] = 2; p.es[0] = 1; p.S[0] = S;
+    p.w[0] = w.pe_flow.proj.w; p.bias[0] = w.pe_flow.proj.b; p.g[0] = w.pe_flow.norm.g; p.b[0] = w.pe_flow.norm.b;
+    p.n_in = 1; p.gf = w.flow_norm.g; p.bf = w.flow_norm.b; p.y = f0; p.B = B; p.E = E;
+    patch_embed(c, p);
+  }
+  basic_layer_impl(c, f0, flow_x, full[0], w.flow_layer, nullptr, B, P, P, 8);
+  void* x0 = f0;  // f0 is dead once the flow layer has run
+  {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
+    PatchEmbedP p;
+    p.img[0] = ogm; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
+    p.w[0] = w.pe_vec.proj.w; p.bias[0] = w.pe_vec.proj.b; p.g[0] = w.pe_vec.norm.g; p.b[0] = w.pe_vec.norm.b;
+    p.img[1] = map_img; p.Cin[1] = 3; p.es[1] = 1; p.S[1] = 256;
+    p.w[1] = w.pe_map.proj.w; p.bias[1] = w.pe_map.proj.b; p.g[1] = w.pe_map.norm.g; p.b[1] = w.pe_map.norm.b;
+    p.n_in = 2; p.pad1 = large ? 32 : 0;
+    p.gf = w.all_patch_norm.g; p.bf = w.all_patch_norm.b; p.y = x0; p.B = B; p.E = E;
+    patch_embed(c, p);
+  }
+  void* x1 = c.alloc_act(B * L0 / 4 * 2 * E);
+  void* x2 = c.alloc_act(B * L0 / 16 * 4 * E);
+  basic_layer_impl(c, x0, x1, full[1], w.layers[0], flow_x, B, P, P, 8);  // + flow_x (modules.py:613)
+  basic_layer_impl(c, x1, x2, full[2], w.layers[1], nullptr, B, P / 2, P / 2, 8);
+  basic_layer_impl(c, x2, nullptr, full[3], w.layers[2], nullptr, B, P / 4, P / 4, 8);
+  if (large) {  // centre crops (modules.py:614-622)
+    center_crop(c, full[0], outs[0], B, P, E);
+    center_crop(c, full[1], outs[1], B, P, E);
+    center_crop(c, full[2], outs[2], B, P / 2, 2 * E);
+    center_crop(c, full[3], outs[3], B, P / 4, 4 * E);
+  }
+  c.ws.release(mark);
+}
+
+// ---- FGMSA.call (FG_MSA.py:106-183) --------------------------------------------------------------
+// y = proj_out(attn) (+ x if add_input); off fp32 [B,8,256,2] and pos are caller-provided
+void fgmsa_impl(Ctx& c, const void* x, void* y, float* off, float* pos, const SjFgmsaW& w, int B, bool add_input) {
+  const int M = B * 256;
+  size_t mark = c.ws.mark();
+  void* qkv = c.alloc_act((size_t)M * 1152);
+  void* o = c.alloc_act((size_t)M * 384);
+  linear(c, x, 384, w.qkv, qkv, 1152, M, 1152, 384, ACT_NONE);
+  fg_offset(c, qkv, 1152, &w, B, off, pos);
+  MhaP p;
+  p.q = qkv; p.k = adv(c, (const void*)qkv, 384); p.v = adv(c, (const void*)qkv, 768);
+  p.ldq = p.ldk = p.ldv = 1152; p.out = o; p.ldo = 384;
+  p.batch = B; p.heads = 8; p.D = 48; p.Nq = 256; p.Nk = 256;
+  p.fg_pos = pos; p.fg_table = w.rpe_table;
+  mha_core(c, p);
+  linear(c, o, 384, w.out, y, 384, M, 384, 384, ACT_NONE, add_input ? x : nullptr, 384);
+  c.ws.release(mark);
+}
+
+// ---- TrajNetCrossAttention.call (trajNet.py:284-319) ---------------------------------------------
+void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void* out, const SjTrajW& w, int B) {
+  const int NA = B * 64, NS = NA * 11;
+  size_t mark = c.ws.mark();
+  void* node = c.alloc_act((size_t)NS * 64);
+  int* stepmask = (int*)c.alloc((size_t)NS * 4);
+  int* cmask = (int*)c.alloc((size_t)NA * 4);
+  float* vec = (float*)c.alloc((size_t)NA * 64 * 4);
+  void* nqkv = c.alloc_act((size_t)NS * 768);
+  void* natt = c.alloc_act((size_t)NS * 256);
+  void* nproj = c.alloc_act((size_t)NS * 320);
+  void* cat = c.alloc_act((size_t)NA * 384);
+  void* E = c.alloc_act((size_t)NA * 384);
+  void* A = c.alloc_act((size_t)NA * 384);
+  void* Q = c.alloc_act((size_t)NA * 384);
+  void* Qp = c.alloc_act((size_t)NA * 384);
+  void* KV = c.alloc_act((size_t)NA * 768);
+  void* O2 = c.alloc_act((size_t)NA * 384);
+  void* V0 = c.alloc_act((size_t)NA * 384);
+  void* F1 = c.alloc_act((size_t)NA * 1536);
+  void* F2 = c.alloc_act((size_t)NA * 384);
+  void* key = c.alloc_act((size_t)NA * 384);
+  float* mean = (float*)c.alloc((size_t)B * 2048 * 4);
+  float* rstd = (float*)c.alloc((size_t)B * 2048 * 4);
+
+  // TrajEncoder over all B*64 actors at once (weights shared, trajNet.py:101,128,132)
+  traj_node(c, obs, occ, &w, B, node, stepmask, cmask, vec);
+  linear(c, node, 64, w.node_qkv, nqkv, 768, NS, 768, 64, ACT_NONE);
+  {
+    MhaP p;
+    p.q = nqkv; p.k = adv(c, (const void*)nqkv, 256); p.v = adv(c, (const void*)nqkv, 512);
+    p.ldq = p.ldk = p.ldv = 768; p.out = natt; p.ldo = 256;
+    p.batch = NA; p.heads = 4; p.D = 64; p.Nq = 11; p.Nk = 11;
+    p.qmask = stepmask; p.kmask = stepmask; p.mask_div = 1;
+    mha_core(c, p);
+  }
+  linear(c, natt, 256, w.node_proj, nproj, 320, NS, 320, 256, ACT_NONE);
+  traj_pool_concat(c, nproj, vec, NA, cat);
+  linear(c, cat, 384, w.sublayer, E, 384, NA, 384, 384, ACT_ELU);
+  // interaction Cross_Attention (trajNet.py:150-176, :79-87)
+  traj_prep(c, E, cmask, w.seg_w, NA, A, Q);
+  linear(c, Q, 384, w.ia_q, Qp, 384, NA, 384, 384, ACT_NONE);
+  linear(c, A, 384, w.ia_kv, KV, 768, NA, 768, 384, ACT_NONE);
+  {
+    MhaP p;
+    p.q = Qp; p.k = KV; p.v = adv(c, (const void*)KV, 384);
+    p.ldq = 384; p.ldk = p.ldv = 768; p.out = O2; p.ldo = 384;
+    p.batch = B; p.heads = 6; p.D = 64; p.Nq = 64; p.Nk = 64;
+    p.qmask = cmask; p.kmask = cmask; p.mask_div = 1;
+    mha_core(c, p);
+  }
+  linear(c, O2, 384, w.ia_proj, V0, 384, NA, 384, 384, ACT_NONE);
+  ln_stats(c, V0, NA, 384, 384, 1e-3f, mean, rstd);
+  {
+    GemmP g;
+    g.A = V0; g.lda = 384; g.W = w.ia_ffn1.w; g.ldw = 1536; g.bias = w.ia_ffn1.b; g.C = F1; g.ldc = 1536;
+    g.M = NA; g.N = 1536; g.K = 384; g.act = ACT_ELU;
+    g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.ia_norm1.g; g.ln_b = w.ia_norm1.b;
+    gemm(c, g);
+  }
+  linear(c, F1, 1536, w.ia_ffn2, F2, 384, NA, 384, 1536, ACT_NONE);
+  traj_final(c, E, F2, &w, NA, key);
+
+  // 8 per-waypoint Cross_AttentionT as grouped launches (trajNet.py:305-314, :224-234)
+  const int MQ = B * 256;
+  void* Qc = c.alloc_act((size_t)B * 2048 * 128);
+  void* KVc = c.alloc_act((size_t)B * 8 * 64 * 256);
+  void* Oc = c.alloc_act((size_t)B * 2048 * 128);
+  void* P1 = c.alloc_act((size_t)B * 2048 * 128);
+  void* Fc = c.alloc_act((size_t)B * 2048 * 512);
+  void* Gc = c.alloc_act((size_t)B * 2048 * 384);
+  RowMap pm;  // rows of a [B,8,256,*] tensor visited per group t
+  pm.inner = 256; pm.outer = 2048; pm.gstride = 256;
+  {
+    GemmP g;
+    g.A = pic; g.lda = 384; g.W = w.ca_q.w; g.ldw = 128; g.w_gstride = 384 * 128; g.C = Qc; g.ldc = 128;
+    g.M = MQ; g.N = 128; g.K = 384; g.groups = 8; g.am = pm; g.cm = pm;
+    gemm(c, g);
+  }
+  {
+    GemmP g;
+    g.A = key; g.lda = 384; g.W = w.ca_kv.w; g.ldw = 256; g.w_gstride = 384 * 256; g.C = KVc; g.ldc = 256;
+    g.M = NA; g.N = 256; g.K = 384; g.groups = 8;
+    g.cm.inner = 64; g.cm.outer = 512; g.cm.gstride = 64;
+    gemm(c, g);
+  }
+  {
+    MhaP p;
+    p.q = Qc; p.k = KVc; p.v = adv(c, (const void*)KVc, 128);
+    p.ldq = 128; p.ldk = p.ldv = 256; p.out = Oc; p.ldo = 128;
+    p.batch = B * 8; p.heads = 3; p.D = 42; p.Nq = 256; p.Nk = 64;
+    p.kmask = cmask; p.mask_div = 8;
+    mha_core(c, p);
+  }
+  {
+    GemmP g;
+    g.A = Oc; g.lda = 128; g.W = w.ca_proj.w; g.ldw = 128; g.w_gstride = 128 * 128; g.bias = w.ca_proj.b;
+    g.bias_gstride = 128; g.C = P1; g.ldc = 128; g.M = MQ; g.N = 128; g.K = 128; g.groups = 8; g.am = pm; g.cm = pm;
+    gemm(c, g);
+  }
+  ln_stats(c, P1, B * 2048, 128, 128, 1e-3f, mean, rstd);
+  {
+    GemmP g;
+    g.A = P1; g.lda = 128; g.W = w.ca_ffn1.w; g.ldw = 512; g.w_gstride = 128 * 512; g.bias = w.ca_ffn1.b;
+    g.bias_gstride = 512; g.C = Fc; g.ldc = 512; g.M = MQ; g.N = 512; g.K = 128; g.groups = 8; g.am = pm; g.cm = pm;
+    g.act = ACT_ELU;
+    g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.ca_norm1.g; g.ln_b = w.ca_norm1.b; g.ln_gstride = 128;
+    gemm(c, g);
+  }
+  {
+    GemmP g;
+    g.A = Fc; g.lda = 512; g.W = w.ca_ffn2.w; g.ldw = 384; g.w_gstride = 512 * 384; g.bias = w.ca_ffn2.b;
+    g.bias_gstride = 384; g.C = Gc; g.ldc = 384; g.M = MQ; g.N = 384; g.K = 512; g.groups = 8; g.am = pm; g.cm = pm;
+    gemm(c, g);
+  }
+  // norm2, then + query[:, t] (trajNet.py:233, :310)
+  layernorm(c, Gc, out, B * 2048, 384, w.ca_norm2.g, w.ca_norm2.b, 1e-3f, pic, 256, 8);
+  c.ws.release(mark);
+}
+
+// ---- Pyramid3DDecoder.call (modules.py:739-772) --------------------------------------------------
+void upconv(Ctx& c, const void* x, void* y, const SjLinear& w, int NB, int Hin, int Cin, int Cout) {
+  GemmP g;
+  g.amode = A_CONV3; g.A = x; g.H = 2 * Hin; g.Wd = 2 * Hin; g.Cin = Cin; g.up = 1;
+  g.W = w.w; g.ldw = Cout; g.bias = w.b; g.C = y; g.ldc = Cout;
+  g.M = NB * 4 * Hin * Hin; g.N = Cout; g.K = 9 * Cin; g.act = ACT_ELU;
+  gemm(c, g);
+}
+// dst[b,t] = src[b,t] + ELU(skip[b] . W_eff[t] + bias): the collapsed (8,1,1) Conv3D
+void res_add(Ctx& c, const void* skip, const SjLinear& w, const void* src, void* dst, int B, int HW, int Cin, int Cout) {
+  GemmP g;
+  g.A = skip; g.lda = Cin; g.W = w.w; g.ldw = Cout; g.w_gstride = (long long)Cin * Cout; g.bias = w.b;
+  g.C = dst; g.ldc = Cout; g.R = src; g.ldr = Cout;
+  g.M = B * HW; g.N = Cout; g.K = Cin; g.groups = 8; g.act = ACT_ELU;
+  g.cm.inner = HW; g.cm.outer = 8 * HW; g.cm.gstride = HW;
+  gemm(c, g);
+}
+
+void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0, const void* res1, float* out,
+                  const SjDecoderW& w, int B, int out_layout) {
+  const int NB = B * 8;
+  size_t mark = c.ws.mark();
+  void* x1 = c.alloc_act((size_t)NB * 32 * 32 * 192);
+  void* x2 = c.alloc_act((size_t)NB * 64 * 64 * 128);
+  void* fx = c.alloc_act((size_t)NB * 64 * 64 * 128);
+  void* x3 = c.alloc_act((size_t)NB * 128 * 128 * 96);
+  void* x4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
+  upconv(c, x, x1, w.upconv[0], NB, 16, 384, 192);
+  res_add(c, res1, w.res[0], x1, x1, B, 32 * 32, 192, 192);
+  upconv(c, x1, x2, w.upconv[1], NB, 32, 192, 128);
+  res_add(c, res0, w.res[1], x2, x2, B, 64 * 64, 96, 128);
+  res_add(c, flow_res, w.res_f, x2, fx, B, 64 * 64, 96, 128);  // uses x AFTER the res0 add (modules.py:762-765)
+  upconv(c, x2, x3, w.upconv[2], NB, 64, 128, 96);
+  upconv(c, x3, x4, w.upconv[3], NB, 128, 96, 48);
+  void* f3 = x3;  // x3 is dead once x4 exists
+  upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96);
+  void* f4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
+  upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48);
+  out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out);
+  c.ws.release(mark);
+}
+
+// ---- STrajNet.call (modules.py:815-839) ----------------------------------------------------------
+void strajnet_impl(Ctx& c, const float* ogm, const float* map_img, const float* flow, const float* obs,
+                   const float* occ, float* out, const SjModelW& w, int B, int S) {
+  size_t mark = c.ws.mark();
+  void* flow_res = c.alloc_act((size_t)B * 4096 * 96);
+  void* res0 = c.alloc_act((size_t)B * 4096 * 96);
+  void* res1 = c.alloc_act((size_t)B * 1024 * 192);
+  void* res2 = c.alloc_act((size_t)B * 256 * 384);
+  void* query = c.alloc_act((size_t)B * 2048 * 384);
+  void* obs_value = c.alloc_act((size_t)B * 2048 * 384);
+  encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm);
+  const void* q2 = res2;
+  float* off = nullptr;
+  if (w.fg_msa) {
+    void* q2b = c.alloc_act((size_t)B * 256 * 384);
+    off = (float*)c.alloc((size_t)B * 4096 * 2 * 4);
+    float* pos = (float*)c.alloc((size_t)B * 4096 * 2 * 4);
+    fgmsa_impl(c, res2, q2b, off, pos, w.fgmsa, B, true);  // q = res + q (modules.py:825)
+    q2 = q2b;
+  }
+  if (w.fg && !w.fg_msa) { c.fail(SJ_EINVAL); return; }
+  build_query(c, q2, off, &w.fgmsa, B, w.fg, query);  // repeat x8 (+ flow_hidden), modules.py:827-831
+  traj_impl(c, query, obs, occ, obs_value, w.traj, B);
+  decoder_impl(c, obs_value, flow_res, res0, res1, out, w.decoder, B, 1);
+  c.ws.release(mark);
+}
+
+// ---- dry-run / real-run drivers -------------------------------------------------------------------
+template <typename F>
+size_t measure(int dtype, F&& body) {
+  Ctx d;
+  d.dry = true;
+  d.dtype = dtype;
+  body(d);
+  return d.ws.high + 256;
+}
+
+template <typename F>
+int run(void* ws, size_t ws_bytes, int dtype, sj_stream_t stream, F&& body) {
+  if (dtype != SJ_F32 && dtype != SJ_BF16) return SJ_EINVAL;
+  Ctx d;
+  d.dry = true;
+  d.dtype = dtype;
+  body(d);
+  if (d.status != SJ_OK) return d.status;
+  if (d.ws.high > 0) {
+    if (!ws || ((uintptr_t)ws & 255)) return ws ? SJ_EINVAL : SJ_EWORKSPACE;
+    if (d.ws.high > ws_bytes) return SJ_EWORKSPACE;
+  }
+  Ctx c;
+  c.dtype = dtype;
+  c.stream = (cudaStream_t)stream;
+  c.ws.base = (char*)ws;
+  c.ws.cap = ws_bytes;
+  body(c);
+  if (c.status == SJ_OK && c.ws.overflow) return SJ_EWORKSPACE;
+  return c.status;
+}
+
+}  // namespace
+}  // namespace sj
+
+using namespace sj;
+
+#define SJ_REQUIRE(cond) \
+  do {                   \
+    if (!(cond)) return SJ_EINVAL; \
+  } while (0)
+
+extern "C" {
+
+int sj_version(void) { return 100; }
+
+size_t sj_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(SjLinear);
+    case 1: return sizeof(SjNorm);
+    case 2: return sizeof(SjSwinBlockW);
+    case 3: return sizeof(SjPatchMergeW);
+    case 4: return sizeof(SjPatchEmbedW);
+    case 5: return sizeof(SjBasicLayerW);
+    case 6: return sizeof(SjEncoderW);
+    case 7: return sizeof(SjFgmsaW);
+    case 8: return sizeof(SjTrajW);
+    case 9: return sizeof(SjDecoderW);
+    case 10: return sizeof(SjModelW);
+    default: return 0;
+  }
+}
+
+const char* sj_strerror(int status) {
+  switch (status) {
+    case SJ_OK: return "ok";
+    case SJ_EINVAL: return "invalid argument (shape, null pointer or alignment)";
+    case SJ_EUNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+    case SJ_ECUDA: return "CUDA error (see sj_last_cuda_error)";
+    case SJ_EWORKSPACE: return "workspace too small or missing";
+    default: return "unknown status";
+  }
+}
+
+const char* sj_last_cuda_error(void) { return tls().cuda_err; }
+
+long long sj_launch_count(int reset) {
+  long long n = tls().launches;
+  if (reset) tls().launches = 0;
+  return n;
+}
+
+int sj_relative_position_index(int ws, int64_t* out, sj_stream_t stream) {
+  SJ_REQUIRE(out && ws > 0 && ws <= 16);
+  return run(nullptr, 0, SJ_F32, stream, [&](Ctx& c) { relative_position_index(c, ws, out); });
+}
+int sj_shift_attn_mask(int H, int W, int ws, int shift, float* out, sj_stream_t stream) {
+  SJ_REQUIRE(out && ws > 0 && H % ws == 0 && W % ws == 0 && shift > 0 && shift < ws);
+  return run(nullptr, 0, SJ_F32, stream, [&](Ctx& c) { shift_attn_mask(c, H, W, ws, shift, out); });
+}
+int sj_window_token_map(int H, int W, int ws, int shift, int32_t* out, sj_stream_t stream) {
+  SJ_REQUIRE(out && ws > 0 && H % ws == 0 && W % ws == 0 && shift >= 0 && shift < ws);
+  return run(nullptr, 0, SJ_F32, stream, [&](Ctx& c) { window_token_map(c, H, W, ws, shift, out); });
+}
+
+static int partition_like(const void* x, void* y, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream,
+                          int scatter) {
+  SJ_REQUIRE(x && y && B > 0 && ws > 0 && H % ws == 0 && W % ws == 0 && C % 4 == 0);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) { window_permute(c, x, y, B, H, W, C, ws, scatter); });
+}
+int sj_window_partition_fwd(const void* x, void* windows, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream) {
+  return partition_like(x, windows, B, H, W, C, ws, dtype, stream, 0);
+}
+int sj_window_reverse_fwd(const void* windows, void* x, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream) {
+  return partition_like(windows, x, B, H, W, C, ws, dtype, stream, 1);
+}
+
+// ---- Mlp ----
+static void mlp_body(Ctx& c, const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2, int M, int C, int hidden) {
+  size_t mark = c.ws.mark();
+  void* h = c.alloc_act((size_t)M * hidden);
+  linear(c, x, C, *fc1, h, hidden, M, hidden, C, ACT_GELU);
+  linear(c, h, hidden, *fc2, y, C, M, C, hidden, ACT_NONE);
+  c.ws.release(mark);
+}
+size_t sj_mlp_workspace_bytes(int M, int C, int hidden, int dtype) {
+  SjLinear z{};
+  return measure(dtype, [&](Ctx& c) { mlp_body(c, nullptr, nullptr, &z, &z, M, C, hidden); });
+}
+int sj_mlp_fwd(const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2, int M, int C, int hidden, int dtype,
+               void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x && y && fc1 && fc2 && fc1->w && fc2->w && M > 0);
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { mlp_body(c, x, y, fc1, fc2, M, C, hidden); });
+}
+
+// ---- WindowAttention ----
+static void wattn_body(Ctx& c, const void* xw, void* y, const SjSwinBlockW* w, int B_, int C, int heads, const float* mask,
+                       int nW) {
+  size_t mark = c.ws.mark();
+  const int M = B_ * 64;
+  void* qkv = c.alloc_act((size_t)M * 3 * C);
+  void* o = c.alloc_act((size_t)M * C);
+  linear(c, xw, C, w->qkv, qkv, 3 * C, M, 3 * C, C, ACT_NONE);
+  window_attn_core(c, qkv, o, w->rpb_table, B_, C, heads, mask ? 2 : 0, 0, 0, 0, mask, nW);
+  linear(c, o, C, w->proj, y, C, M, C, C, ACT_NONE);
+  c.ws.release(mark);
+}
+size_t sj_window_attention_workspace_bytes(int B_, int C, int dtype) {
+  SjSwinBlockW z{};
+  return measure(dtype, [&](Ctx& c) { wattn_body(c, nullptr, nullptr, &z, B_, C, 1, nullptr, 0); });
+}
+int sj_window_attention_fwd(const void* xw, void* y, const SjSwinBlockW* w, int B_, int C, int heads, int ws,
+                            const float* mask, int nW, int dtype, void* workspace, size_t workspace_bytes,
+                            sj_stream_t stream) {
+  SJ_REQUIRE(xw && y && w && w->qkv.w && w->proj.w && w->rpb_table && B_ > 0 && heads > 0);
+  if (ws != 8 || C % 16) return SJ_EUNSUPPORTED;
+  if (mask && (nW <= 0 || B_ % nW)) return SJ_EINVAL;
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { wattn_body(c, xw, y, w, B_, C, heads, mask, nW); });
+}
+
+// ---- SwinTransformerBlock ----
+size_t sj_swin_block_workspace_bytes(int B, int H, int W, int C, int dtype) {
+  SjSwinBlockW z{};
+  return measure(dtype, [&](Ctx& c) { swin_block_impl(c, nullptr, nullptr, z, B, H, W, C, 1, 8, 0, nullptr); });
+}
+int sj_swin_block_fwd(const void* x, void* y, const SjSwinBlockW* w, int B, int H, int W, int C, int heads, int ws,
+                      int shift, int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x && y && w && B > 0);
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { swin_block_impl(c, x, y, *w, B, H, W, C, heads, ws, shift, nullptr); });
+}
+
+// ---- PatchMerging ----
+size_t sj_patch_merging_workspace_bytes(int B, int H, int W, int C, int dtype) {
+  SjPatchMergeW z{};
+  return measure(dtype, [&](Ctx& c) { patch_merging_impl(c, nullptr, nullptr, z, nullptr, B, H, W, C); });
+}
+int sj_patch_merging_fwd(const void* x, void* y, const SjPatchMergeW* w, const void* add, int B, int H, int W, int C,
+                         int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x && y && w && B > 0);
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { patch_merging_impl(c, x, y, *w, add, B, H, W, C); });
+}
+
+// ---- PatchEmbed ----
+int sj_patch_embed_fwd(const float* img, void* y, const SjPatchEmbedW* w, int B, int S, int Cin, int elem_stride, int E,
+                       int dtype, sj_stream_t stream) {
+  SJ_REQUIRE(img && y && w && B > 0 && elem_stride >= 1);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) {
+    PatchEmbedP p;
+    p.img[0] = img; p.Cin[0] = Cin; p.es[0] = elem_stride; p.S[0] = S;
+    p.w[0] = w->proj.w; p.bias[0] = w->proj.b; p.g[0] = w->norm.g; p.b[0] = w->norm.b;
+    p.n_in = 1; p.y = y; p.B = B; p.E = E;
+    patch_embed(c, p);
+  });
+}
+
+// ---- BasicLayer ----
+size_t sj_basic_layer_workspace_bytes(int B, int H, int W, int C, int dtype) {
+  SjSwinBlockW zb[2] = {};
+  SjBasicLayerW z{};
+  z.blocks_host = zb; z.depth = 2; z.dim = C; z.heads = 1; z.has_down = 1;
+  return measure(dtype, [&](Ctx& c) { basic_layer_impl(c, nullptr, (void*)1, (void*)1, z, nullptr, B, H, W, 8); });
+}
+int sj_basic_layer_fwd(const void* x, void* y_down, void* res, const SjBasicLayerW* w, int B, int H, int W, int ws,
+                       int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x && res && w && B > 0);
+  if (ws != 8) return SJ_EUNSUPPORTED;
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { basic_layer_impl(c, x, y_down, res, *w, nullptr, B, H, W, ws); });
+}
+
+// ---- Encoder ----
+static void fake_encoder(SjEncoderW& e, SjSwinBlockW* zb) {
+  memset(&e, 0, sizeof(e));
+  e.num_layers = 3; e.window_size = 8; e.embed_dim = 96;
+  e.flow_layer.blocks_host = zb; e.flow_layer.depth = 2; e.flow_layer.dim = 96; e.flow_layer.heads = 3; e.flow_layer.has_down = 1;
+  for (int i = 0; i < 3; ++i) {
+    e.layers[i].blocks_host = zb; e.layers[i].depth = 2; e.layers[i].dim = 96 << i; e.layers[i].heads = 3 << i;
+    e.layers[i].has_down = i < 2;
+  }
+}
+size_t sj_encoder_workspace_bytes(int B, int S, int dtype) {
+  SjSwinBlockW zb[2] = {};
+  SjEncoderW e;
+  fake_encoder(e, zb);
+  return measure(dtype, [&](Ctx& c) {
+    encoder_impl(c, nullptr, nullptr, nullptr, (void*)1, (void*)1, (void*)1, (void*)1, e, B, S, S == 512);
+  });
+}
+int sj_encoder_fwd(const float* ogm, const float* map_img, const float* flow, void* flow_res, void* res0, void* res1,
+                   void* res2, const SjEncoderW* w, int B, int S, int large_input, int dtype, void* workspace,
+                   size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(ogm && map_img && flow && flow_res && res0 && res1 && res2 && w && B > 0);
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) {
+    encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, *w, B, S, large_input);
+  });
+}
+
+// ---- FGMSA ----
+static void fgmsa_body(Ctx& c, const void* x, void* y, float* pos, void* flow_hidden, const SjFgmsaW* w, int B) {
+  size_t mark = c.ws.mark();
+  float* off = (float*)c.alloc((size_t)B * 4096 * 2 * 4);
+  fgmsa_impl(c, x, y, off, pos, *w, B, false);
+  if (flow_hidden) fg_flow_hidden(c, off, w, B, flow_hidden);
+  c.ws.release(mark);
+}
+size_t sj_fgmsa_workspace_bytes(int B, int dtype) {
+  SjFgmsaW z{};
+  return measure(dtype, [&](Ctx& c) { fgmsa_body(c, nullptr, nullptr, nullptr, nullptr, &z, B); });
+}
+int sj_fgmsa_fwd(const void* x, void* y, float* pos, void* flow_hidden, const SjFgmsaW* w, int B, int dtype,
+                 void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x && y && pos && w && B > 0);
+  if (flow_hidden && (!w->offproj2_w || !w->offproj2_b)) return SJ_EINVAL;
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { fgmsa_body(c, x, y, pos, flow_hidden, w, B); });
+}
+
+// ---- TrajNetCrossAttention ----
+size_t sj_traj_cross_attention_workspace_bytes(int B, int dtype) {
+  SjTrajW z{};
+  return measure(dtype, [&](Ctx& c) { traj_impl(c, nullptr, nullptr, nullptr, nullptr, z, B); });
+}
+int sj_traj_cross_attention_fwd(const void* pic, const float* obs, const float* occ, void* out, const SjTrajW* w, int B,
+                                int dtype, void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(pic && obs && occ && out && w && B > 0);
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { traj_impl(c, pic, obs, occ, out, *w, B); });
+}
+
+// ---- Pyramid3DDecoder ----
+size_t sj_decoder_workspace_bytes(int B, int dtype) {
+  SjDecoderW z{};
+  return measure(dtype, [&](Ctx& c) { decoder_impl(c, nullptr, nullptr, nullptr, nullptr, nullptr, z, B, 1); });
+}
+int sj_decoder_fwd(const void* x, const void* flow_res, const void* res0, const void* res1, float* out,
+                   const SjDecoderW* w, int B, int out_layout, int dtype, void* workspace, size_t workspace_bytes,
+                   sj_stream_t stream) {
+  SJ_REQUIRE(x && flow_res && res0 && res1 && out && w && B > 0 && (out_layout == 0 || out_layout == 1));
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { decoder_impl(c, x, flow_res, res0, res1, out, *w, B, out_layout); });
+}
+
+// ---- STrajNet ----
+size_t sj_strajnet_workspace_bytes(int B, int S, int dtype) {
+  SjSwinBlockW zb[2] = {};
+  SjModelW m;
+  memset(&m, 0, sizeof(m));
+  fake_encoder(m.encoder, zb);
+  m.fg_msa = 1; m.fg = 1; m.large_ogm = (S == 512);
+  return measure(dtype, [&](Ctx& c) { strajnet_impl(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m, B, S); });
+}
+int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, const float* obs, const float* occ,
+                    float* out, const SjModelW* w, int B, int S, int dtype, void* workspace, size_t workspace_bytes,
+                    sj_stream_t stream) {
+  SJ_REQUIRE(ogm && map_img && flow && obs && occ && out && w && B > 0);
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { strajnet_impl(c, ogm, map_img, flow, obs, occ, out, *w, B, S); });
+}
+
+}  // extern "C"

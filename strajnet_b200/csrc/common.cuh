@@ -1,0 +1,130 @@
+// Shared device/host helpers for the strajnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/strajnet_b200.h"
+
+namespace sj {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- per-thread library state ---------------------------------------------------------------
+struct TlsState {
+  long long launches = 0;
+  char cuda_err[256] = {0};
+};
+TlsState& tls();
+
+// ---- execution context: stream, activation dtype, workspace arena ---------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  bool overflow = false;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > high) high = off;
+    if (base == nullptr || off > cap) {
+      overflow = true;
+      return nullptr;
+    }
+    return base + a;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  int dtype = SJ_F32;
+  bool dry = false;  // dry run: only size the workspace, launch nothing
+  Arena ws;
+  int status = SJ_OK;
+  size_t esize() const { return dtype == SJ_BF16 ? 2 : 4; }
+  void* alloc(size_t bytes) { return ws.alloc(bytes); }
+  // element-count allocation in the activation dtype
+  void* alloc_act(size_t n) { return ws.alloc(n * esize()); }
+  bool ok() const { return status == SJ_OK; }
+  void fail(int s) {
+    if (status == SJ_OK) status = s;
+  }
+};
+
+// records a launch, and the CUDA error if one is pending
+void note_launch(Ctx& c, const char* what);
+
+#define SJ_LAUNCH(ctx, what, kernel, grid, block, smem, ...)                 \
+  do {                                                                      \
+    if (!(ctx).dry && (ctx).ok()) {                                         \
+      kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);       \
+      sj::note_launch((ctx), what);                                         \
+    }                                                                       \
+  } while (0)
+
+// ---- typed element access --------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (pointer must be 4-element aligned)
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4<bf16>(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, float4 v);
+template <> __device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void st4<bf16>(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---- math --------------------------------------------------------------------------------------
+// tanh-GELU exactly as modules.py:18-29
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k = 0.7978845608028654f;  // sqrt(2/pi)
+  float u = k * (x + 0.044715f * x * x * x);
+  return x * (0.5f * (1.0f + tanhf(u)));
+}
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_ELU = 2 };
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_GELU) return gelu_tanh(v);
+  if (act == ACT_ELU) return elu1(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Region id of the shifted-window mask image (modules.py:192-203) at position (y, x) of the
+// *shifted* image: rows/cols split at H-ws and H-shift, id = 3*rowband + colband.
+__host__ __device__ __forceinline__ int shift_region_id(int H, int W, int ws, int shift, int y, int x) {
+  int by = y < H - ws ? 0 : (y < H - shift ? 1 : 2);
+  int bx = x < W - ws ? 0 : (x < W - shift ? 1 : 2);
+  return by * 3 + bx;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace sj

@@ -1,0 +1,126 @@
+// Internal launcher interface between the C-ABI sequencing code (api.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace sj {
+
+// ---- generic GEMM / implicit-conv (gemm_simt.cu) ----------------------------------------------
+enum AMode { A_PLAIN = 0, A_CONV3 = 1, A_MERGE = 2 };
+
+// row = (m / inner) * outer + (m % inner) + group * gstride, then optionally through a gather map
+// applied within blocks of map_len rows.  inner == 0 means identity.
+struct RowMap {
+  int inner = 0, outer = 0, gstride = 0;
+  const int* map = nullptr;
+  int map_len = 0;
+};
+
+struct GemmP {
+  int amode = A_PLAIN;
+  const void* A = nullptr;
+  int lda = 0;
+  const float* W = nullptr;  // [K,N] fp32
+  int ldw = 0;
+  long long w_gstride = 0;
+  const float* bias = nullptr;
+  int bias_gstride = 0;
+  void* C = nullptr;
+  int ldc = 0;
+  const void* R = nullptr;  // residual added after the activation, indexed like C
+  int ldr = 0;
+  int M = 0, N = 0, K = 0, groups = 1;
+  RowMap am, cm;
+  // LayerNorm applied to A on load: (a - mean[row]) * rstd[row] * g[k] + b[k]
+  const float* ln_mean = nullptr;
+  const float* ln_rstd = nullptr;
+  const float* ln_g = nullptr;
+  const float* ln_b = nullptr;
+  int ln_gstride = 0;
+  int act = ACT_NONE;
+  // A_CONV3: output H x Wd, input (H>>up) x (Wd>>up) x Cin, M = images*H*Wd, K = 9*Cin
+  // A_MERGE: input H x Wd x Cin, M = B*(H/2)*(Wd/2), K = 4*Cin
+  int H = 0, Wd = 0, Cin = 0, up = 0;
+};
+void gemm(Ctx& c, const GemmP& p);
+
+// ---- LayerNorm family (norm.cu) ---------------------------------------------------------------
+// per-row mean / rstd (biased variance) of x[rows, C] (row stride ld)
+void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* mean, float* rstd);
+// stats of the PatchMerging gather (modules.py:282-287) of x [B,H,W,C]: rows = B*H/2*W/2, width 4C
+void ln_stats_merge(Ctx& c, const void* x, int B, int H, int W, int C, float eps, float* mean, float* rstd);
+// y = LN(x) * g + b (+ res); gamma/beta of group ((row / g_div) % g_mod)
+void layernorm(Ctx& c, const void* x, void* y, int rows, int C, const float* g, const float* b, float eps,
+               const void* res, int g_div, int g_mod);
+
+// ---- attention cores (attention.cu) -----------------------------------------------------------
+// Window attention core, modules.py:109-131.  qkv [nWinTotal*64, 3C] (q|k|v, head-major inside),
+// out [nWinTotal*64, C].  mask_mode 0: none; 1: shifted-window mask computed from (H,W,ws,shift);
+// 2: explicit mask tensor [nW,64,64].
+void window_attn_core(Ctx& c, const void* qkv, void* out, const float* rpb_table, int n_windows_total, int C,
+                      int heads, int mask_mode, int H, int W, int shift, const float* mask, int nW);
+// Generic multi-head attention core with tfa semantics: logits = (q/sqrt(D)) . k,
+// + (-1e10) where (qmask*kmask)==0, softmax, . v.  q rows [batch*Nq] with stride ldq (head h at column
+// h*D), same for k, v (batch*Nk rows).  out [batch*Nq, ldo], columns >= heads*D zero-filled.
+// kmask index = (batch / mask_div) * Nk + key;  qmask index = (batch / mask_div) * Nq + query.
+struct MhaP {
+  const void *q = nullptr, *k = nullptr, *v = nullptr;
+  void* out = nullptr;
+  int ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  int batch = 0, heads = 0, D = 0, Nq = 0, Nk = 0;
+  const int* qmask = nullptr;
+  const int* kmask = nullptr;
+  int mask_div = 1;
+  // FG-MSA bias (FG_MSA.py:150-172): pos fp32 [batch, heads, Nk, 2], rpe_table [31,31,heads]; 16x16 grid
+  const float* fg_pos = nullptr;
+  const float* fg_table = nullptr;
+};
+void mha_core(Ctx& c, const MhaP& p);
+
+// ---- everything else (misc.cu) ----------------------------------------------------------------
+void relative_position_index(Ctx& c, int ws, int64_t* out);
+void shift_attn_mask(Ctx& c, int H, int W, int ws, int shift, float* out);
+void window_token_map(Ctx& c, int H, int W, int ws, int shift, int32_t* out);
+// window_partition (scatter 0) / window_reverse (scatter 1) on data (modules.py:49-63)
+void window_permute(Ctx& c, const void* x, void* y, int B, int H, int W, int C, int ws, int scatter);
+
+// Fused patch embedding (modules.py:437-446, :576-587, :602): for each token
+//   y = LN_final( sum_i LN_i(conv4x4s4_i(img_i) + b_i) ), second input optional.
+// Input i: fp32 [B,S_i,S_i,Cin_i] with channel element stride es_i.  The token grid is P x P with
+// P = S_0/4; input 1 may cover only the centre (pad1 > 0: tokens outside [pad1, P-pad1) get 0 from it).
+struct PatchEmbedP {
+  const float* img[2] = {nullptr, nullptr};
+  int Cin[2] = {0, 0}, es[2] = {1, 1}, S[2] = {0, 0};
+  const float* w[2] = {nullptr, nullptr};   // [16*Cin, E]
+  const float* bias[2] = {nullptr, nullptr};
+  const float* g[2] = {nullptr, nullptr};
+  const float* b[2] = {nullptr, nullptr};
+  int n_in = 1, pad1 = 0;
+  const float* gf = nullptr;  // final LN (NULL: skip)
+  const float* bf = nullptr;
+  void* y = nullptr;
+  int B = 0, E = 0;
+};
+void patch_embed(Ctx& c, const PatchEmbedP& p);
+
+// FG-MSA offset network (FG_MSA.py:84-92, :114-117, :134): q rows [B*256, ldq] (first 384 columns)
+// -> off fp32 [B,8,256,2] (8*tanh), pos = off + (j,i)
+void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos);
+// flow_hidden [B,8,256,384] = off . Wp2 + bp2 (FG_MSA.py:120-123)
+void fg_flow_hidden(Ctx& c, const float* off, const SjFgmsaW* w, int B, void* out);
+// query [B,8,256,384] = q2[b,l,:] (+ off . Wp2 + bp2 if fg)   (modules.py:827-831)
+void build_query(Ctx& c, const void* q2, const float* off, const SjFgmsaW* w, int B, int fg, void* query);
+
+// trajectory glue (trajNet.py:38-48, :127-155, :179-185)
+void traj_node(Ctx& c, const float* obs, const float* occ, const SjTrajW* w, int B, void* node, int* stepmask,
+               int* cmask, float* vec);
+void traj_pool_concat(Ctx& c, const void* proj, const float* vec, int n_actors, void* cat);
+void traj_prep(Ctx& c, const void* E, const int* cmask, const float* seg_w, int n_actors, void* A, void* Q);
+void traj_final(Ctx& c, const void* E, const void* F2, const SjTrajW* w, int n_actors, void* key);
+
+// decoder head: two 3x3 48->2 convs (modules.py:767-770) written straight into the final layout
+void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, const float* b, int B, int out_layout,
+              float* out);
+// crop the centre of x [B,P,P,C] -> y [B,P/2,P/2,C] (modules.py:614-622)
+void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
+
+}  // namespace sj

@@ -1,0 +1,482 @@
+// Index maps, data reshuffles, patch embedding, FG-MSA offset network, trajectory glue and the
+// decoder head.  All HBM-/latency-bound CUDA-core work.
+#include "kernels.h"
+
+namespace sj {
+namespace {
+
+// ---------------------------------------------------------------- integer maps (bit-exact rows)
+__global__ void rel_pos_index_kernel(int ws, int64_t* out) {
+  int N = ws * ws;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  int n = i / N, m = i % N;
+  out[i] = (int64_t)((n / ws - m / ws + ws - 1) * (2 * ws - 1) + (n % ws - m % ws + ws - 1));
+}
+
+__global__ void shift_mask_kernel(int H, int W, int ws, int shift, float* out) {
+  int N = ws * ws;
+  long long total = (long long)(H / ws) * (W / ws) * N * N;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int m = i % N, n = (i / N) % N, w = i / ((long long)N * N);
+  int wy = (w / (W / ws)) * ws, wx = (w % (W / ws)) * ws;
+  int a = shift_region_id(H, W, ws, shift, wy + n / ws, wx + n % ws);
+  int b = shift_region_id(H, W, ws, shift, wy + m / ws, wx + m % ws);
+  out[i] = (a != b) ? -100.0f : 0.0f;
+}
+
+__global__ void window_token_map_kernel(int H, int W, int ws, int shift, int32_t* out) {
+  int N = ws * ws;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int w = i / N, n = i % N;
+  int y = ((w / (W / ws)) * ws + n / ws + shift) % H;
+  int x = ((w % (W / ws)) * ws + n % ws + shift) % W;
+  out[i] = y * W + x;
+}
+
+// window_partition (scatter = 0) / window_reverse (scatter = 1) on data, modules.py:49-63
+template <typename T>
+__global__ void window_permute_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C, int H, int W,
+                                      int ws, int scatter) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c4 = C / 4;
+  if (i >= rows * c4) return;
+  long long r = i / c4;  // row in window order: ((b*nW + w)*ws*ws + n)
+  int c = (i % c4) * 4;
+  int L = H * W, N = ws * ws;
+  int l = r % L;
+  int w = l / N, n = l % N;
+  int yy = (w / (W / ws)) * ws + n / ws, xx = (w % (W / ws)) * ws + n % ws;
+  long long mr = (r / L) * L + yy * W + xx;
+  if (scatter) st4<T>(y + mr * C + c, ld4<T>(x + r * C + c));
+  else st4<T>(y + r * C + c, ld4<T>(x + mr * C + c));
+}
+
+template <typename T>
+__global__ void center_crop_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int P, int C) {
+  int h = P / 2, o = P / 4, c4 = C / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * h * h * c4) return;
+  int c = (i % c4) * 4;
+  long long t = i / c4;
+  int xx = t % h, yy = (t / h) % h, b = t / ((long long)h * h);
+  st4<T>(y + t * C + c, ld4<T>(x + (((long long)b * P + yy + o) * P + xx + o) * C + c));
+}
+
+// ---------------------------------------------------------------- fused patch embedding (K3)
+constexpr int PE_TOK = 8;
+constexpr int PE_KMAX = 16 * 11;
+
+template <typename T>
+__global__ void patch_embed_kernel(const PatchEmbedP p) {
+  __shared__ float ins[PE_TOK][PE_KMAX];
+  __shared__ float vals[PE_TOK][128];
+  __shared__ float stat[PE_TOK][2];
+  const int n = threadIdx.x, E = p.E;
+  const int P = p.S[0] / 4;
+  const long long tok0 = (long long)blockIdx.x * PE_TOK;
+  const long long ntok = (long long)p.B * P * P;
+  const int nwarps = blockDim.x / 32, warp = n / 32, lane = n % 32;
+  float total[PE_TOK];
+#pragma unroll
+  for (int t = 0; t < PE_TOK; ++t) total[t] = 0.f;
+
+  auto row_stats = [&]() {  // LN statistics of vals[t][0..E) for each token, one warp per token
+    __syncthreads();
+    for (int t = warp; t < PE_TOK; t += nwarps) {
+      float s = 0.f;
+      for (int i = lane; i < E; i += 32) s += vals[t][i];
+      float mu = warp_sum(s) / E;
+      float q = 0.f;
+      for (int i = lane; i < E; i += 32) {
+        float d = vals[t][i] - mu;
+        q += d * d;
+      }
+      float var = warp_sum(q) / E;
+      if (lane == 0) {
+        stat[t][0] = mu;
+        stat[t][1] = rsqrtf(var + 1e-5f);
+      }
+    }
+    __syncthreads();
+  };
+
+  for (int in = 0; in < p.n_in; ++in) {
+    const int Cin = p.Cin[in], es = p.es[in], S = p.S[in], K = 16 * Cin;
+    const int pad = in == 1 ? p.pad1 : 0;
+    __syncthreads();
+    for (int i = n; i < PE_TOK * K; i += blockDim.x) {
+      int t = i / K, k = i % K;
+      long long tok = tok0 + t;
+      float v = 0.f;
+      if (tok < ntok) {
+        int pj = tok % P, pi = (tok / P) % P, b = tok / ((long long)P * P);
+        pi -= pad;
+        pj -= pad;
+        if (pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4) {
+          int c = k % Cin, kx = (k / Cin) % 4, ky = k / (4 * Cin);
+          v = p.img[in][((((long long)b * S + 4 * pi + ky) * S + 4 * pj + kx) * Cin + c) * es];
+        }
+      }
+      ins[t][k] = v;
+    }
+    __syncthreads();
+    float acc[PE_TOK];
+#pragma unroll
+    for (int t = 0; t < PE_TOK; ++t) acc[t] = 0.f;
+    if (n < E) {
+      const float* w = p.w[in] + n;
+      for (int k = 0; k < K; ++k) {
+        float wv = w[(long long)k * E];
+#pragma unroll
+        for (int t = 0; t < PE_TOK; ++t) acc[t] = fmaf(ins[t][k], wv, acc[t]);
+      }
+      float bv = p.bias[in][n];
+#pragma unroll
+      for (int t = 0; t < PE_TOK; ++t) vals[t][n] = acc[t] + bv;
+    }
+    row_stats();
+    if (n < E) {
+      float gv = p.g[in][n], bv = p.b[in][n];
+#pragma unroll
+      for (int t = 0; t < PE_TOK; ++t) {
+        long long tok = tok0 + t;
+        bool inside = true;
+        if (pad > 0 && tok < ntok) {
+          int pj = tok % P - pad, pi = (tok / P) % P - pad;
+          inside = pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4;
+        }
+        if (inside) total[t] += (vals[t][n] - stat[t][0]) * stat[t][1] * gv + bv;
+      }
+    }
+  }
+  if (p.gf) {
+    __syncthreads();
+    if (n < E)
+#pragma unroll
+      for (int t = 0; t < PE_TOK; ++t) vals[t][n] = total[t];
+    row_stats();
+    if (n < E) {
+      float gv = p.gf[n], bv = p.bf[n];
+#pragma unroll
+      for (int t = 0; t < PE_TOK; ++t) total[t] = (vals[t][n] - stat[t][0]) * stat[t][1] * gv + bv;
+    }
+  }
+  if (n < E) {
+    T* y = reinterpret_cast<T*>(p.y);
+#pragma unroll
+    for (int t = 0; t < PE_TOK; ++t)
+      if (tok0 + t < ntok) stf<T>(y + (tok0 + t) * E + n, total[t]);
+  }
+}
+
+// ---------------------------------------------------------------- FG-MSA offset network
+// one block (384 threads) per (b, pixel) of the 16x16 grid
+template <typename T>
+__global__ void __launch_bounds__(384) fg_offset_kernel(const T* __restrict__ q, int ldq, SjFgmsaW w,
+                                                        float* __restrict__ off, float* __restrict__ pos) {
+  __shared__ float qs[9][384];
+  __shared__ float us[384];
+  __shared__ float red[12];
+  const int n = threadIdx.x, b = blockIdx.x / 256, pix = blockIdx.x % 256, i = pix / 16, j = pix % 16;
+  for (int tap = 0; tap < 9; ++tap) {
+    int yy = i + tap / 3 - 1, xx = j + tap % 3 - 1;
+    qs[tap][n] = (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) ? ldf<T>(q + ((long long)b * 256 + yy * 16 + xx) * ldq + n) : 0.f;
+  }
+  __syncthreads();
+  const int g = n / 48;
+  float acc = w.conv0_b[n];
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* wt = w.conv0_w + (long long)tap * 48 * 384 + n;
+    const float* qv = &qs[tap][g * 48];
+#pragma unroll 8
+    for (int cc = 0; cc < 48; ++cc) acc = fmaf(qv[cc], wt[cc * 384], acc);
+  }
+  // LayerNorm over 384 channels, eps 1e-3 (Keras default), then tanh-GELU
+  const int warp = n / 32, lane = n % 32;
+  float s = warp_sum(acc);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float mu = 0.f;
+  for (int k = 0; k < 12; ++k) mu += red[k];
+  mu /= 384.f;
+  __syncthreads();
+  float d = acc - mu;
+  float s2 = warp_sum(d * d);
+  if (lane == 0) red[warp] = s2;
+  __syncthreads();
+  float var = 0.f;
+  for (int k = 0; k < 12; ++k) var += red[k];
+  var /= 384.f;
+  float u = d * rsqrtf(var + 1e-3f) * w.conv_norm.g[n] + w.conv_norm.b[n];
+  us[n] = gelu_tanh(u);
+  __syncthreads();
+  if (n < 16) {
+    int gg = n / 2, o = n % 2;
+    float a = 0.f;
+    for (int cc = 0; cc < 48; ++cc) a = fmaf(us[gg * 48 + cc], w.offproj_w[cc * 2 + o], a);
+    a = tanhf(a) * 8.0f;  // offset_range = (Hk/2, Wk/2) = (8, 8), FG_MSA.py:115-117
+    long long idx = (((long long)b * 8 + gg) * 256 + pix) * 2 + o;
+    off[idx] = a;
+    pos[idx] = a + (o == 0 ? (float)j : (float)i);  // tf.meshgrid 'xy': ref[i,j] = (j, i)
+  }
+}
+
+template <typename T>
+__global__ void build_query_kernel(const T* __restrict__ q2, const float* __restrict__ off, const float* __restrict__ w2,
+                                   const float* __restrict__ b2, int B, int fg, T* __restrict__ query) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*8*256*96 float4 groups
+  if (i >= (long long)B * 8 * 256 * 96) return;
+  int c = (i % 96) * 4;
+  long long row = i / 96;  // (b*8 + t)*256 + l
+  int l = row % 256;
+  long long b = row / 2048;
+  float4 v = q2 ? ld4<T>(q2 + (b * 256 + l) * 384 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (fg) {
+    float o0 = off[row * 2], o1 = off[row * 2 + 1];
+    float4 w0 = *reinterpret_cast<const float4*>(w2 + c), w1 = *reinterpret_cast<const float4*>(w2 + 384 + c);
+    float4 bb = *reinterpret_cast<const float4*>(b2 + c);
+    // flow_hidden = off . Wp2 + bp2 is formed first, then added to the query (modules.py:830-831)
+    v.x += fmaf(o1, w1.x, o0 * w0.x) + bb.x;
+    v.y += fmaf(o1, w1.y, o0 * w0.y) + bb.y;
+    v.z += fmaf(o1, w1.z, o0 * w0.z) + bb.z;
+    v.w += fmaf(o1, w1.w, o0 * w0.w) + bb.w;
+  }
+  st4<T>(query + row * 384 + c, v);
+}
+
+// ---------------------------------------------------------------- trajectory glue
+// one block (64 threads) per actor: node features, step masks, type embedding
+template <typename T>
+__global__ void traj_node_kernel(const float* __restrict__ obs, const float* __restrict__ occ, SjTrajW w, int B,
+                                 T* __restrict__ node, int* __restrict__ stepmask, int* __restrict__ cmask,
+                                 float* __restrict__ vec) {
+  __shared__ float X[88];
+  const int a = blockIdx.x, b = a / 64, i = a % 64, n = threadIdx.x;
+  const float* src = i < 48 ? obs + ((long long)b * 48 + i) * 88 : occ + ((long long)b * 16 + (i - 48)) * 88;
+  for (int k = n; k < 88; k += 64) X[k] = src[k];
+  __syncthreads();
+  if (n < 11) stepmask[a * 11 + n] = X[n * 8] != 0.f;
+  if (n == 0) {
+    int any = 0;
+    for (int t = 0; t < 11; ++t) any |= X[t * 8] != 0.f;
+    cmask[a] = any;
+  }
+  float wn[5];
+#pragma unroll
+  for (int cc = 0; cc < 5; ++cc) wn[cc] = w.node_w[cc * 64 + n];
+  float bn = w.node_b[n];
+  for (int t = 0; t < 11; ++t) {
+    float acc = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) acc = fmaf(X[t * 8 + cc], wn[cc], acc);
+    stf<T>(node + ((long long)a * 11 + t) * 64 + n, elu1(acc + bn));
+  }
+  float v = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) v = fmaf(X[5 + cc], w.vec_w[cc * 64 + n], v);
+  vec[(long long)a * 64 + n] = v;
+}
+
+template <typename T>
+__global__ void traj_pool_concat_kernel(const T* __restrict__ proj, const float* __restrict__ vec, T* __restrict__ cat) {
+  const int a = blockIdx.x, n = threadIdx.x;  // 384 threads
+  float v;
+  if (n < 320) {
+    v = -INFINITY;
+    for (int t = 0; t < 11; ++t) v = fmaxf(v, ldf<T>(proj + ((long long)a * 11 + t) * 320 + n));  // mask-unaware (Q6)
+  } else {
+    v = vec[(long long)a * 64 + n - 320];
+  }
+  stf<T>(cat + (long long)a * 384 + n, v);
+}
+
+template <typename T>
+__global__ void traj_prep_kernel(const T* __restrict__ E, const int* __restrict__ cmask, const float* __restrict__ seg_w,
+                                 T* __restrict__ A, T* __restrict__ Q) {
+  const int a = blockIdx.x, n = threadIdx.x;  // 384 threads
+  float e = ldf<T>(E + (long long)a * 384 + n) * (float)cmask[a];
+  float s = seg_w[((a % 64) < 48 ? 0 : 384) + n];
+  stf<T>(A + (long long)a * 384 + n, e);
+  stf<T>(Q + (long long)a * 384 + n, e + s);
+}
+
+// key[a] = LN(E[a] + LN(F2[a]; ia_norm2) + seg; obs_norm | occ_norm), eps 1e-3.  One warp per actor.
+template <typename T>
+__global__ void traj_final_kernel(const T* __restrict__ E, const T* __restrict__ F2, SjTrajW w, int n_actors,
+                                  T* __restrict__ key) {
+  int a = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (a >= n_actors) return;
+  float f[12], s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    f[k] = ldf<T>(F2 + (long long)a * 384 + lane + 32 * k);
+    s += f[k];
+  }
+  float mu = warp_sum(s) / 384.f, q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) q += (f[k] - mu) * (f[k] - mu);
+  float rs = rsqrtf(warp_sum(q) / 384.f + 1e-3f);
+  const bool is_obs = (a % 64) < 48;
+  const SjNorm nm = is_obs ? w.obs_norm : w.occ_norm;
+  s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    int n = lane + 32 * k;
+    float val = (f[k] - mu) * rs * w.ia_norm2.g[n] + w.ia_norm2.b[n];
+    // obs = obs + val_obs (trajNet.py:179), then obs + embed (:184)
+    f[k] = (ldf<T>(E + (long long)a * 384 + n) + val) + w.seg_w[(is_obs ? 0 : 384) + n];
+    s += f[k];
+  }
+  mu = warp_sum(s) / 384.f;
+  q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) q += (f[k] - mu) * (f[k] - mu);
+  rs = rsqrtf(warp_sum(q) / 384.f + 1e-3f);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    int n = lane + 32 * k;
+    stf<T>(key + (long long)a * 384 + n, (f[k] - mu) * rs * nm.g[n] + nm.b[n]);
+  }
+}
+
+// ---------------------------------------------------------------- decoder head (K10)
+// thread per output pixel of one waypoint image; both 48->2 convs; writes 4 floats
+template <typename T>
+__global__ void out_conv_kernel(const T* __restrict__ xo, const T* __restrict__ xf, const float* __restrict__ w,
+                                const float* __restrict__ bias, int NB, int out_layout, float* __restrict__ out) {
+  __shared__ __align__(16) float ws[2 * 432 * 2];
+  for (int i = threadIdx.x; i < 2 * 432 * 2; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)NB * 65536) return;
+  int x = i % 256, y = (i / 256) % 256;
+  long long img = i / 65536;
+  float r[4] = {bias[0], bias[1], bias[2], bias[3]};
+#pragma unroll
+  for (int head = 0; head < 2; ++head) {
+    const T* src = head == 0 ? xo : xf;
+    const float* wh = ws + head * 864;
+    float a0 = 0.f, a1 = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= 256 || xx < 0 || xx >= 256) continue;
+      const T* px = src + ((img * 256 + yy) * 256 + xx) * 48;
+      const float* wt = wh + tap * 96;
+#pragma unroll
+      for (int c = 0; c < 48; c += 4) {
+        float4 v = ld4<T>(px + c);
+        a0 = fmaf(v.x, wt[2 * c], a0);     a1 = fmaf(v.x, wt[2 * c + 1], a1);
+        a0 = fmaf(v.y, wt[2 * c + 2], a0); a1 = fmaf(v.y, wt[2 * c + 3], a1);
+        a0 = fmaf(v.z, wt[2 * c + 4], a0); a1 = fmaf(v.z, wt[2 * c + 5], a1);
+        a0 = fmaf(v.w, wt[2 * c + 6], a0); a1 = fmaf(v.w, wt[2 * c + 7], a1);
+      }
+    }
+    r[head * 2] += a0;
+    r[head * 2 + 1] += a1;
+  }
+  long long o;
+  if (out_layout == 0) o = i * 4;                       // [B,8,256,256,4]
+  else {
+    long long b = img / 8;
+    int t = img % 8;
+    o = ((b * 256 + y) * 256 + x) * 32 + t * 4;         // [B,256,256,32], channel t*4+c (modules.py:838)
+  }
+  *reinterpret_cast<float4*>(out + o) = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- launchers
+void relative_position_index(Ctx& c, int ws, int64_t* out) {
+  if (!c.ok() || c.dry) return;
+  int n = ws * ws * ws * ws;
+  SJ_LAUNCH(c, "rel_pos_index", rel_pos_index_kernel, cdiv(n, 256), 256, 0, ws, out);
+}
+void shift_attn_mask(Ctx& c, int H, int W, int ws, int shift, float* out) {
+  if (!c.ok() || c.dry) return;
+  long long total = (long long)(H / ws) * (W / ws) * ws * ws * ws * ws;
+  SJ_LAUNCH(c, "shift_mask", shift_mask_kernel, cdiv(total, 256), 256, 0, H, W, ws, shift, out);
+}
+void window_token_map(Ctx& c, int H, int W, int ws, int shift, int32_t* out) {
+  if (!c.ok() || c.dry) return;
+  SJ_LAUNCH(c, "window_token_map", window_token_map_kernel, cdiv(H * W, 256), 256, 0, H, W, ws, shift, out);
+}
+void window_permute(Ctx& c, const void* x, void* y, int B, int H, int W, int C, int ws, int scatter) {
+  if (!c.ok() || c.dry) return;
+  if (C % 4) { c.fail(SJ_EINVAL); return; }
+  long long rows = (long long)B * H * W, n = rows * (C / 4);
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "window_permute", window_permute_kernel<bf16>, cdiv(n, 256), 256, 0, (const bf16*)x, (bf16*)y, rows, C, H, W, ws, scatter);
+  else SJ_LAUNCH(c, "window_permute", window_permute_kernel<float>, cdiv(n, 256), 256, 0, (const float*)x, (float*)y, rows, C, H, W, ws, scatter);
+}
+void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C) {
+  if (!c.ok() || c.dry) return;
+  long long n = (long long)B * (P / 2) * (P / 2) * (C / 4);
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "center_crop", center_crop_kernel<bf16>, cdiv(n, 256), 256, 0, (const bf16*)x, (bf16*)y, B, P, C);
+  else SJ_LAUNCH(c, "center_crop", center_crop_kernel<float>, cdiv(n, 256), 256, 0, (const float*)x, (float*)y, B, P, C);
+}
+
+void patch_embed(Ctx& c, const PatchEmbedP& p) {
+  if (!c.ok() || c.dry) return;
+  if (p.E > 128 || p.E % 32 || p.n_in < 1 || p.n_in > 2) { c.fail(SJ_EUNSUPPORTED); return; }
+  for (int i = 0; i < p.n_in; ++i)
+    if (p.Cin[i] > 11 || p.S[i] % 4) { c.fail(SJ_EUNSUPPORTED); return; }
+  int P = p.S[0] / 4;
+  long long ntok = (long long)p.B * P * P;
+  int grid = cdiv(ntok, PE_TOK);
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "patch_embed", patch_embed_kernel<bf16>, grid, p.E, 0, p);
+  else SJ_LAUNCH(c, "patch_embed", patch_embed_kernel<float>, grid, p.E, 0, p);
+}
+
+void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {
+  if (!c.ok() || c.dry) return;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<bf16>, B * 256, 384, 0, (const bf16*)q, ldq, *w, off, pos);
+  else SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<float>, B * 256, 384, 0, (const float*)q, ldq, *w, off, pos);
+}
+void build_query(Ctx& c, const void* q2, const float* off, const SjFgmsaW* w, int B, int fg, void* query) {
+  if (!c.ok() || c.dry) return;
+  long long n = (long long)B * 8 * 256 * 96;
+  const float* w2 = fg ? w->offproj2_w : nullptr;
+  const float* b2 = fg ? w->offproj2_b : nullptr;
+  if (fg && (!w2 || !b2 || !off)) { c.fail(SJ_EINVAL); return; }
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "build_query", build_query_kernel<bf16>, cdiv(n, 256), 256, 0, (const bf16*)q2, off, w2, b2, B, fg, (bf16*)query);
+  else SJ_LAUNCH(c, "build_query", build_query_kernel<float>, cdiv(n, 256), 256, 0, (const float*)q2, off, w2, b2, B, fg, (float*)query);
+}
+void fg_flow_hidden(Ctx& c, const float* off, const SjFgmsaW* w, int B, void* out) {
+  build_query(c, nullptr, off, w, B, 1, out);
+}
+
+void traj_node(Ctx& c, const float* obs, const float* occ, const SjTrajW* w, int B, void* node, int* stepmask,
+               int* cmask, float* vec) {
+  if (!c.ok() || c.dry) return;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "traj_node", traj_node_kernel<bf16>, B * 64, 64, 0, obs, occ, *w, B, (bf16*)node, stepmask, cmask, vec);
+  else SJ_LAUNCH(c, "traj_node", traj_node_kernel<float>, B * 64, 64, 0, obs, occ, *w, B, (float*)node, stepmask, cmask, vec);
+}
+void traj_pool_concat(Ctx& c, const void* proj, const float* vec, int n_actors, void* cat) {
+  if (!c.ok() || c.dry) return;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "traj_pool_concat", traj_pool_concat_kernel<bf16>, n_actors, 384, 0, (const bf16*)proj, vec, (bf16*)cat);
+  else SJ_LAUNCH(c, "traj_pool_concat", traj_pool_concat_kernel<float>, n_actors, 384, 0, (const float*)proj, vec, (float*)cat);
+}
+void traj_prep(Ctx& c, const void* E, const int* cmask, const float* seg_w, int n_actors, void* A, void* Q) {
+  if (!c.ok() || c.dry) return;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "traj_prep", traj_prep_kernel<bf16>, n_actors, 384, 0, (const bf16*)E, cmask, seg_w, (bf16*)A, (bf16*)Q);
+  else SJ_LAUNCH(c, "traj_prep", traj_prep_kernel<float>, n_actors, 384, 0, (const float*)E, cmask, seg_w, (float*)A, (float*)Q);
+}
+void traj_final(Ctx& c, const void* E, const void* F2, const SjTrajW* w, int n_actors, void* key) {
+  if (!c.ok() || c.dry) return;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "traj_final", traj_final_kernel<bf16>, cdiv(n_actors, 8), 256, 0, (const bf16*)E, (const bf16*)F2, *w, n_actors, (bf16*)key);
+  else SJ_LAUNCH(c, "traj_final", traj_final_kernel<float>, cdiv(n_actors, 8), 256, 0, (const float*)E, (const float*)F2, *w, n_actors, (float*)key);
+}
+
+void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, const float* b, int B, int out_layout,
+              float* out) {
+  if (!c.ok() || c.dry) return;
+  int NB = B * 8;
+  long long n = (long long)NB * 65536;
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "out_conv", out_conv_kernel<bf16>, cdiv(n, 128), 128, 0, (const bf16*)x_occ, (const bf16*)x_flow, w, b, NB, out_layout, out);
+  else SJ_LAUNCH(c, "out_conv", out_conv_kernel<float>, cdiv(n, 128), 128, 0, (const float*)x_occ, (const float*)x_flow, w, b, NB, out_layout, out);
+}
+
+}  // namespace sj

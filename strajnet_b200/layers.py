@@ -1,0 +1,594 @@
+"""Host-side mirror of the reference's Keras layers (same constructor arguments, `build()` /
+`call()` protocol and error behaviour), executing through the C ABI in libstrajnet_b200.so.
+
+Each class cites the reference class it replaces.  Tensors are torch CUDA tensors (NumPy arrays
+and CPU tensors are copied to the device); PyTorch is used only for device memory and streams.
+Inference only: `training=True` raises (dropout / DropPath are never active on the reference's
+inference path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import weights as W
+
+Tensor = torch.Tensor
+_DT = {"float32": (L.SJ_F32, torch.float32), "fp32": (L.SJ_F32, torch.float32),
+       "bfloat16": (L.SJ_BF16, torch.bfloat16), "bf16": (L.SJ_BF16, torch.bfloat16)}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _inference_only(training) -> None:
+    if training:
+        raise NotImplementedError("strajnet_b200 implements the inference path only: call with training=False")
+
+
+class Layer:
+    """Minimal Keras-like layer: weights in Keras layout by attribute path, lazy `build()`."""
+
+    def __init__(self, dtype: str = "float32", device="cuda"):
+        if dtype not in _DT:
+            raise ValueError(f"dtype must be one of {sorted(_DT)}")
+        self.sj_dtype, self.act_dtype = _DT[dtype]
+        self.device = torch.device(device)
+        self.weights: Dict[str, Tensor] = {}
+        self.built = False
+        self._packed = None
+        self._ws: Optional[Tensor] = None
+
+    # -- weights ---------------------------------------------------------------------------------
+    def weight_shapes(self) -> Dict[str, tuple]:
+        raise NotImplementedError
+
+    def build(self, input_shape=None) -> None:
+        if not self.weights:
+            self.weights = W.default_init(self.weight_shapes())
+        self.built = True
+
+    def set_weights(self, weights: Dict[str, Tensor]) -> None:
+        shapes = self.weight_shapes()
+        missing = [k for k in shapes if k not in weights]
+        if missing:
+            raise ValueError(f"missing weights: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        new = {}
+        for k, shp in shapes.items():
+            t = torch.as_tensor(weights[k]).detach().to(torch.float32).cpu()
+            if tuple(t.shape) != tuple(shp):
+                raise ValueError(f"weight '{k}' has shape {tuple(t.shape)}, expected {tuple(shp)}")
+            new[k] = t
+        self.weights = new
+        self._packed = None
+        self.built = True
+
+    def get_weights(self) -> Dict[str, Tensor]:
+        if not self.built:
+            self.build()
+        return dict(self.weights)
+
+    def save_weights(self, path: str) -> None:
+        np.savez(path, **{k: v.numpy() for k, v in self.get_weights().items()})
+
+    def load_weights(self, path: str) -> None:
+        with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+            self.set_weights({k: torch.from_numpy(z[k]) for k in z.files})
+
+    # -- execution helpers -----------------------------------------------------------------------
+    def _packer(self) -> W.Packer:
+        return W.Packer(self.weights, self.device, tc=self.sj_dtype == L.SJ_BF16)
+
+    def _pack(self):
+        raise NotImplementedError
+
+    def packed(self):
+        if not self.built:
+            self.build()
+        if self._packed is None:
+            self._packed = self._pack()
+        return self._packed[0]
+
+    def _workspace(self, nbytes: int) -> Tuple[Optional[int], int]:
+        if nbytes == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def _act(self, x, shape=None) -> Tensor:
+        t = torch.as_tensor(x).to(device=self.device, dtype=self.act_dtype).contiguous()
+        if shape is not None and tuple(t.shape[1:]) != tuple(shape):
+            raise ValueError(f"input has shape {tuple(t.shape)}, expected [B,{','.join(map(str, shape))}]")
+        return t
+
+    def _f32(self, x, shape=None) -> Tensor:
+        t = torch.as_tensor(x).to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None and tuple(t.shape[1:]) != tuple(shape):
+            raise ValueError(f"input has shape {tuple(t.shape)}, expected [B,{','.join(map(str, shape))}]")
+        return t
+
+    def _new(self, *shape) -> Tensor:
+        return torch.empty(*shape, dtype=self.act_dtype, device=self.device)
+
+    def __call__(self, *a, **k):
+        if not self.built:
+            self.build()
+        return self.call(*a, **k)
+
+
+# ------------------------------------------------------------------------------------------------
+def window_partition(x: Tensor, window_size: int) -> Tensor:
+    """modules.py:49-55 on the GPU: [B,H,W,C] -> [B*nW, ws, ws, C]."""
+    B, H, Wd, Cc = x.shape
+    dt = L.SJ_BF16 if x.dtype == torch.bfloat16 else L.SJ_F32
+    x = x.contiguous()
+    y = torch.empty(B * (H // window_size) * (Wd // window_size), window_size, window_size, Cc, dtype=x.dtype, device=x.device)
+    L.check(L.lib().sj_window_partition_fwd(x.data_ptr(), y.data_ptr(), B, H, Wd, Cc, window_size, dt, _stream()),
+            "window_partition")
+    return y
+
+
+def window_reverse(windows: Tensor, window_size: int, H: int, Wd: int, Cc: int) -> Tensor:
+    """modules.py:58-63 on the GPU."""
+    B = windows.shape[0] // ((H // window_size) * (Wd // window_size))
+    dt = L.SJ_BF16 if windows.dtype == torch.bfloat16 else L.SJ_F32
+    windows = windows.contiguous()
+    x = torch.empty(B, H, Wd, Cc, dtype=windows.dtype, device=windows.device)
+    L.check(L.lib().sj_window_reverse_fwd(windows.data_ptr(), x.data_ptr(), B, H, Wd, Cc, window_size, dt, _stream()),
+            "window_reverse")
+    return x
+
+
+def relative_position_index(window_size: int, device="cuda") -> Tensor:
+    """WindowAttention.build, modules.py:88-100 (int64 [ws^2, ws^2]), computed on the device."""
+    n = window_size * window_size
+    out = torch.empty(n, n, dtype=torch.int64, device=device)
+    L.check(L.lib().sj_relative_position_index(window_size, out.data_ptr(), _stream()), "relative_position_index")
+    return out
+
+
+def shift_attn_mask(H: int, Wd: int, window_size: int, shift_size: int, device="cuda") -> Tensor:
+    """SwinTransformerBlock.build, modules.py:189-214 (fp32 [nW, ws^2, ws^2] in {0,-100})."""
+    n = window_size * window_size
+    out = torch.empty((H // window_size) * (Wd // window_size), n, n, dtype=torch.float32, device=device)
+    L.check(L.lib().sj_shift_attn_mask(H, Wd, window_size, shift_size, out.data_ptr(), _stream()), "shift_attn_mask")
+    return out
+
+
+def window_token_map(H: int, Wd: int, window_size: int, shift_size: int, device="cuda") -> Tensor:
+    """roll(-shift) + window_partition as an int32 gather map over the H*W tokens."""
+    out = torch.empty(H * Wd, dtype=torch.int32, device=device)
+    L.check(L.lib().sj_window_token_map(H, Wd, window_size, shift_size, out.data_ptr(), _stream()), "window_token_map")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+class Mlp(Layer):
+    """modules.py:31-46."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0., prefix='', **kw):
+        super().__init__(**kw)
+        self.in_features = in_features
+        self.hidden = hidden_features or in_features
+        self.out_features = out_features or in_features
+        if self.out_features != in_features:
+            raise ValueError("Mlp: out_features != in_features is not used by the reference path")
+
+    def weight_shapes(self):
+        return {"fc1.kernel": (self.in_features, self.hidden), "fc1.bias": (self.hidden,),
+                "fc2.kernel": (self.hidden, self.in_features), "fc2.bias": (self.in_features,)}
+
+    def _pack(self):
+        p = self._packer()
+        fc1 = p.linear(p.get("fc1.kernel"), p.get("fc1.bias"))
+        fc2 = p.linear(p.get("fc2.kernel"), p.get("fc2.bias"))
+        return (fc1, fc2), p
+
+    def call(self, x, training=False):
+        _inference_only(training)
+        x = self._act(x)
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
+        fc1, fc2 = self.packed()
+        y = torch.empty_like(x)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_mlp_workspace_bytes(M, Cc, self.hidden, self.sj_dtype))
+        L.check(lib.sj_mlp_fwd(x.data_ptr(), y.data_ptr(), C.byref(fc1), C.byref(fc2), M, Cc, self.hidden,
+                               self.sj_dtype, ws, n, _stream()), "Mlp")
+        return y
+
+
+class WindowAttention(Layer):
+    """modules.py:66-134.  call(x [B_,N,C], mask [nW,N,N] or None)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.,
+                 prefix='', **kw):
+        super().__init__(**kw)
+        if not qkv_bias or qk_scale is not None:
+            raise ValueError("WindowAttention: only qkv_bias=True, qk_scale=None (the reference configuration)")
+        self.dim, self.window_size, self.num_heads = dim, tuple(window_size), num_heads
+        self.relative_position_index = None
+
+    def weight_shapes(self):
+        s = W.swin_block_shapes(self.dim, self.num_heads, self.window_size[0])
+        return {k[len("attn."):]: v for k, v in s.items() if k.startswith("attn.")}
+
+    def build(self, input_shape=None):
+        super().build(input_shape)
+        self.relative_position_index = relative_position_index(self.window_size[0], self.device)
+
+    def _pack(self):
+        p = self._packer()
+        s = L.SjSwinBlockW()
+        s.qkv = p.linear(p.get("qkv.kernel"), p.get("qkv.bias"))
+        s.rpb_table = p.ptr(p.get("relative_position_bias_table"))
+        s.proj = p.linear(p.get("proj.kernel"), p.get("proj.bias"))
+        return s, p
+
+    def call(self, x, mask=None, training=False):
+        _inference_only(training)
+        x = self._act(x)
+        B_, N, Cc = x.shape
+        if N != self.window_size[0] * self.window_size[1] or Cc != self.dim:
+            raise ValueError(f"WindowAttention: input {tuple(x.shape)} does not match window {self.window_size}, dim {self.dim}")
+        m_ptr, nW = None, 0
+        if mask is not None:
+            mask = self._f32(mask)
+            nW = mask.shape[0]
+            m_ptr = mask.data_ptr()
+        y = torch.empty_like(x)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_window_attention_workspace_bytes(B_, Cc, self.sj_dtype))
+        L.check(lib.sj_window_attention_fwd(x.data_ptr(), y.data_ptr(), C.byref(self.packed()), B_, Cc, self.num_heads,
+                                            self.window_size[0], m_ptr, nW, self.sj_dtype, ws, n, _stream()),
+                "WindowAttention")
+        return y
+
+
+class SwinTransformerBlock(Layer):
+    """modules.py:163-262.  call(x [B, H*W, C])."""
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path_prob=0., norm_layer=None, prefix='', **kw):
+        super().__init__(**kw)
+        self.dim, self.input_resolution, self.num_heads = dim, tuple(input_resolution), num_heads
+        self.window_size, self.shift_size, self.mlp_ratio = window_size, shift_size, mlp_ratio
+        if min(self.input_resolution) <= self.window_size:  # modules.py:173-175
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if mlp_ratio != 4. or not qkv_bias or qk_scale is not None:
+            raise ValueError("SwinTransformerBlock: only mlp_ratio=4, qkv_bias=True, qk_scale=None are implemented")
+        self.attn_mask = None
+
+    def weight_shapes(self):
+        return W.swin_block_shapes(self.dim, self.num_heads, self.window_size, self.mlp_ratio)
+
+    def build(self, input_shape=None):
+        super().build(input_shape)
+        if self.shift_size > 0:
+            H, Wd = self.input_resolution
+            self.attn_mask = shift_attn_mask(H, Wd, self.window_size, self.shift_size, self.device)
+
+    def _pack(self):
+        p = self._packer()
+        return p.swin_block(""), p
+
+    def call(self, x, training=False):
+        _inference_only(training)
+        H, Wd = self.input_resolution
+        x = self._act(x)
+        B, Lt, Cc = x.shape
+        assert Lt == H * Wd, f"input feature has wrong size,{H},{Wd},{Lt},{H*Wd}"
+        if Cc != self.dim:
+            raise ValueError(f"SwinTransformerBlock: channel dim {Cc} != {self.dim}")
+        y = torch.empty_like(x)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_swin_block_workspace_bytes(B, H, Wd, Cc, self.sj_dtype))
+        L.check(lib.sj_swin_block_fwd(x.data_ptr(), y.data_ptr(), C.byref(self.packed()), B, H, Wd, Cc, self.num_heads,
+                                      self.window_size, self.shift_size, self.sj_dtype, ws, n, _stream()),
+                "SwinTransformerBlock")
+        return y
+
+
+class PatchMerging(Layer):
+    """modules.py:265-292."""
+
+    def __init__(self, input_resolution, dim, norm_layer=None, prefix='', **kw):
+        super().__init__(**kw)
+        self.input_resolution, self.dim = tuple(input_resolution), dim
+
+    def weight_shapes(self):
+        return W.patch_merging_shapes(self.dim)
+
+    def _pack(self):
+        p = self._packer()
+        return p.patch_merge(""), p
+
+    def call(self, x):
+        H, Wd = self.input_resolution
+        x = self._act(x)
+        B, Lt, Cc = x.shape
+        assert Lt == H * Wd, "input feature has wrong size"
+        assert H % 2 == 0 and Wd % 2 == 0, f"x size ({H}*{Wd}) are not even."
+        y = self._new(B, Lt // 4, 2 * Cc)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_patch_merging_workspace_bytes(B, H, Wd, Cc, self.sj_dtype))
+        L.check(lib.sj_patch_merging_fwd(x.data_ptr(), y.data_ptr(), C.byref(self.packed()), None, B, H, Wd, Cc,
+                                         self.sj_dtype, ws, n, _stream()), "PatchMerging")
+        return y
+
+
+class PatchEmbed(Layer):
+    """modules.py:417-446 (norm_layer is always LayerNormalization in the reference path)."""
+
+    def __init__(self, img_size=(224, 224), patch_size=(4, 4), in_chans=3, embed_dim=96, norm_layer=True, **kw):
+        super().__init__(**kw)
+        if tuple(patch_size) != (4, 4) or norm_layer is None:
+            raise ValueError("PatchEmbed: only patch_size=(4,4) with a LayerNormalization is implemented")
+        self.img_size, self.patch_size, self.in_chans, self.embed_dim = tuple(img_size), (4, 4), in_chans, embed_dim
+        self.patches_resolution = [img_size[0] // 4, img_size[1] // 4]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+
+    def weight_shapes(self):
+        return W.patch_embed_shapes(self.in_chans, self.embed_dim)
+
+    def _pack(self):
+        p = self._packer()
+        return p.patch_embed(""), p
+
+    def call(self, x):
+        x = self._f32(x)
+        B, H, Wd, Cc = x.shape
+        if H != Wd or Cc != self.in_chans:
+            raise ValueError(f"PatchEmbed: input {tuple(x.shape)} must be square with {self.in_chans} channels")
+        y = self._new(B, (H // 4) * (Wd // 4), self.embed_dim)
+        L.check(L.lib().sj_patch_embed_fwd(x.data_ptr(), y.data_ptr(), C.byref(self.packed()), B, H, Cc, 1,
+                                           self.embed_dim, self.sj_dtype, _stream()), "PatchEmbed")
+        return y
+
+
+class BasicLayer(Layer):
+    """modules.py:317-364.  call(x) -> (x_down or x, res)."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop=0., attn_drop=0., drop_path_prob=0., norm_layer=None, downsample=None, use_checkpoint=False,
+                 prefix='', trajnet=False, **kw):
+        dk = {k: kw.pop(k) for k in ("dtype", "device") if k in kw}
+        super().__init__(**dk)
+        if trajnet:
+            raise ValueError("BasicLayer: trajnet=True references an undefined class in the reference (modules.py:349)")
+        self.dim, self.input_resolution, self.depth = dim, tuple(input_resolution), depth
+        self.num_heads, self.window_size = num_heads, window_size
+        self.has_down = downsample is not None
+
+    def weight_shapes(self):
+        return W.basic_layer_shapes(self.dim, self.num_heads, self.depth, self.has_down, self.window_size)
+
+    def _pack(self):
+        p = self._packer()
+        return p.basic_layer("", self.dim, self.num_heads, self.depth, self.has_down), p
+
+    def call(self, x, traj=None, mask=None, mapt=None, map_mask=None, training=False):
+        _inference_only(training)
+        H, Wd = self.input_resolution
+        x = self._act(x)
+        B, Lt, Cc = x.shape
+        assert Lt == H * Wd, "input feature has wrong size"
+        res = torch.empty_like(x)
+        y = self._new(B, Lt // 4, 2 * Cc) if self.has_down else None
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_basic_layer_workspace_bytes(B, H, Wd, Cc, self.sj_dtype))
+        L.check(lib.sj_basic_layer_fwd(x.data_ptr(), y.data_ptr() if y is not None else None, res.data_ptr(),
+                                       C.byref(self.packed()), B, H, Wd, self.window_size, self.sj_dtype, ws, n, _stream()),
+                "BasicLayer")
+        return (y, res) if self.has_down else (res, res)
+
+
+class SwinTransformerEncoder(Layer):
+    """modules.py:448-628 as configured by STrajNet (sep_encode=flow_sep=use_flow=True)."""
+
+    def __init__(self, model_name='swin_tiny_patch4_window7_224', include_top=False, img_size=(224, 224),
+                 patch_size=(4, 4), in_chans=3, num_classes=1000, embed_dim=96, depths=[2, 2, 6, 2],
+                 num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, norm_layer=None, ape=False, patch_norm=True,
+                 use_checkpoint=False, sep_encode=False, no_map=False, flow_sep=False, use_flow=False,
+                 large_input=False, **kw):
+        super().__init__(**kw)
+        if not (sep_encode and flow_sep and use_flow) or no_map or ape:
+            raise ValueError("SwinTransformerEncoder: only the STrajNet wiring (sep_encode=flow_sep=use_flow=True, "
+                             "no_map=False, ape=False; modules.py:782-785) is implemented")
+        self.cfg = dict(input_size=tuple(img_size), window_size=window_size, embed_dim=embed_dim,
+                        depths=list(depths), num_heads=list(num_heads))
+        self.large_input = large_input
+        self.num_layers = len(depths)
+
+    def weight_shapes(self):
+        c = self.cfg
+        return W.encoder_shapes(c["embed_dim"], c["depths"], c["num_heads"], c["window_size"])
+
+    def _pack(self):
+        p = self._packer()
+        return p.encoder("", self.cfg), p
+
+    def call(self, x, map_img, flow, training=True):
+        # `training` never reaches the Swin blocks in the reference (Q3); nothing to disable here
+        S = self.cfg["input_size"][0]
+        ogm = self._f32(x, (S, S, 11, 2))
+        map_img = self._f32(map_img, (256, 256, 3))
+        flow = self._f32(flow, (S, S, 2))
+        B = ogm.shape[0]
+        outs = [self._new(B, 4096, 96), self._new(B, 4096, 96), self._new(B, 1024, 192), self._new(B, 16, 16, 384)]
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_encoder_workspace_bytes(B, S, self.sj_dtype))
+        L.check(lib.sj_encoder_fwd(ogm.data_ptr(), map_img.data_ptr(), flow.data_ptr(), *[o.data_ptr() for o in outs],
+                                   C.byref(self.packed()), B, S, int(self.large_input), self.sj_dtype, ws, n, _stream()),
+                "SwinTransformerEncoder")
+        return outs
+
+
+class FGMSA(Layer):
+    """FG_MSA.py:20-183.  call(x [B,16,16,384]) -> (y, pos, flow_hidden | reference)."""
+
+    def __init__(self, q_size, kv_size, n_heads, n_head_channels, n_groups=6, attn_drop=0., proj_drop=0., stride=1,
+                 offset_range_factor=2, use_pe=True, dwc_pe=False, no_off=False, fixed_pe=False, stage_idx=3,
+                 use_last_ref=False, out_dim=384, fg=False, in_dim=384, **kw):
+        super().__init__(**kw)
+        ok = (tuple(q_size) == (16, 16) and tuple(kv_size) == (16, 16) and n_heads == 8 and n_head_channels == 48
+              and n_groups == 8 and stride == 1 and offset_range_factor > 0 and use_pe and not dwc_pe and not no_off
+              and not fixed_pe and stage_idx == 3 and not use_last_ref and out_dim == 384 and in_dim == 384)
+        if not ok:
+            raise ValueError("FGMSA: only the STrajNet configuration (modules.py:799) is implemented")
+        self.fg = fg
+
+    def weight_shapes(self):
+        return W.fgmsa_shapes(self.fg)
+
+    def _pack(self):
+        p = self._packer()
+        return p.fgmsa("", self.fg), p
+
+    def call(self, x, training=True, last_reference=None):
+        x = self._act(x, (16, 16, 384))  # dropout rates are 0.0 (FG_MSA.py:23): training has no effect
+        B = x.shape[0]
+        y = torch.empty_like(x)
+        pos = torch.empty(B, 8, 16, 16, 2, dtype=torch.float32, device=self.device)
+        hidden = self._new(B, 8, 16, 16, 384) if self.fg else None
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_fgmsa_workspace_bytes(B, self.sj_dtype))
+        L.check(lib.sj_fgmsa_fwd(x.data_ptr(), y.data_ptr(), pos.data_ptr(), hidden.data_ptr() if self.fg else None,
+                                 C.byref(self.packed()), B, self.sj_dtype, ws, n, _stream()), "FGMSA")
+        if self.fg:
+            return y, pos, hidden
+        ii, jj = torch.meshgrid(torch.arange(16, device=self.device), torch.arange(16, device=self.device), indexing="ij")
+        ref = torch.stack((jj, ii), -1).to(torch.float32)[None, None].expand(B, 8, -1, -1, -1).contiguous()
+        return y, pos, ref
+
+
+class TrajNetCrossAttention(Layer):
+    """trajNet.py:236-319 (actor_only=True, sep_actors=False, multi_modal=True)."""
+
+    def __init__(self, traj_cfg, pic_size=(8, 8), pic_dim=768, past_to_current_steps=11, obs_actors=48, occ_actors=16,
+                 actor_only=True, multi_modal=True, sep_actors=False, **kw):
+        super().__init__(**kw)
+        ok = (tuple(pic_size) == (16, 16) and pic_dim == 384 and past_to_current_steps == 11 and obs_actors == 48
+              and occ_actors == 16 and actor_only and multi_modal and not sep_actors
+              and traj_cfg.get("traj_heads") == 4 and traj_cfg.get("att_heads") == 6 and traj_cfg.get("out_dim") == 384
+              and not traj_cfg.get("no_attn", False))
+        if not ok:
+            raise ValueError("TrajNetCrossAttention: only the STrajNet configuration (modules.py:788-795) is implemented")
+
+    def weight_shapes(self):
+        return W.traj_shapes()
+
+    def _pack(self):
+        p = self._packer()
+        return p.traj(""), p
+
+    def call(self, pic_encode, obs_traj, occ_traj, map_traj=None, training=True, flow_pic_encode=None):
+        _inference_only(training)
+        pic = self._act(pic_encode, (8, 16, 16, 384))
+        obs = self._f32(obs_traj, (48, 11, 8))
+        occ = self._f32(occ_traj, (16, 11, 8))
+        B = pic.shape[0]
+        out = torch.empty_like(pic)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_traj_cross_attention_workspace_bytes(B, self.sj_dtype))
+        L.check(lib.sj_traj_cross_attention_fwd(pic.data_ptr(), obs.data_ptr(), occ.data_ptr(), out.data_ptr(),
+                                                C.byref(self.packed()), B, self.sj_dtype, ws, n, _stream()),
+                "TrajNetCrossAttention")
+        return out
+
+
+class Pyramid3DDecoder(Layer):
+    """modules.py:630-772 with the flags STrajNet passes (:800-801)."""
+
+    def __init__(self, config, img_size, use_pyramid=False, model_name='PyrDecoder', split_pred=False,
+                 timestep_split=False, double_decode=False, stp_grad=False, shallow_decode=0, flow_sep_decode=False,
+                 conv_cnn=False, sep_conv=False, rep_res=True, fg_sep=False, **kw):
+        super().__init__(**kw)
+        if not (use_pyramid and flow_sep_decode and shallow_decode == 1 and rep_res) or conv_cnn or sep_conv:
+            raise ValueError("Pyramid3DDecoder: only the STrajNet configuration (use_pyramid, flow_sep_decode, "
+                             "shallow_decode=1, conv_cnn=False; modules.py:800-801) is implemented")
+
+    def weight_shapes(self):
+        return W.decoder_shapes()
+
+    def _pack(self):
+        p = self._packer()
+        return p.decoder(""), p
+
+    def call(self, x, training=True, res_list=None):
+        x = self._act(x, (8, 16, 16, 384))  # no dropout in the decoder: training has no effect
+        if res_list is None or len(res_list) != 4:
+            raise ValueError("Pyramid3DDecoder: res_list must be [flow_res, res0, res1, res2]")
+        flow_res = self._act(res_list[0], (4096, 96))
+        res0 = self._act(res_list[1], (4096, 96))
+        res1 = self._act(res_list[2], (1024, 192))
+        B = x.shape[0]
+        out = torch.empty(B, 8, 256, 256, 4, dtype=torch.float32, device=self.device)
+        lib = L.lib()
+        ws, n = self._workspace(lib.sj_decoder_workspace_bytes(B, self.sj_dtype))
+        L.check(lib.sj_decoder_fwd(x.data_ptr(), flow_res.data_ptr(), res0.data_ptr(), res1.data_ptr(), out.data_ptr(),
+                                   C.byref(self.packed()), B, 0, self.sj_dtype, ws, n, _stream()), "Pyramid3DDecoder")
+        return out
+
+
+class STrajNet(Layer):
+    """modules.py:777-839: the drop-in object.  model(ogm, map_img, training=False, obs=..., occ=..., mapt=..., flow=...)."""
+
+    def __init__(self, cfg, model_name='STrajNet', use_pyramid=True, actor_only=True, sep_actors=False, fg_msa=False,
+                 use_last_ref=False, fg=False, large_ogm=True, **kw):
+        super().__init__(**kw)
+        if not use_pyramid or not actor_only or sep_actors or use_last_ref:
+            raise ValueError("STrajNet: only use_pyramid=True, actor_only=True, sep_actors=False, use_last_ref=False")
+        if fg and not fg_msa:
+            raise ValueError("STrajNet: fg=True needs fg_msa=True (modules.py:828-831 reads `ref` from the FG-MSA layer)")
+        self.cfg = dict(cfg)
+        self.cfg["input_size"] = tuple(cfg["input_size"])
+        if len(cfg["depths"]) != 3 or cfg["embed_dim"] != 96 or cfg["window_size"] != 8:
+            raise ValueError("STrajNet: the decoder hard-codes the 3-stage / 96-dim / window-8 geometry (modules.py:583-585,636)")
+        S = self.cfg["input_size"][0]
+        if (large_ogm and S != 512) or (not large_ogm and S != 256):
+            raise ValueError("STrajNet: input_size 512 needs large_ogm=True and 256 needs large_ogm=False (SURVEY Q13)")
+        self.fg_msa, self.fg, self.large_ogm = fg_msa, fg, large_ogm
+        self._graphs = {}
+
+    def weight_shapes(self):
+        return W.model_shapes(self.cfg, self.fg_msa, self.fg)
+
+    def _pack(self):
+        p = self._packer()
+        return p.model(self.cfg, self.fg_msa, self.fg, self.large_ogm), p
+
+    def workspace_bytes(self, B: int) -> int:
+        return L.lib().sj_strajnet_workspace_bytes(B, self.cfg["input_size"][0], self.sj_dtype)
+
+    def forward_into(self, out: Tensor, ogm: Tensor, map_img: Tensor, obs: Tensor, occ: Tensor, flow: Tensor) -> Tensor:
+        """Launch the forward on the current stream with caller-owned device buffers (graph-capturable)."""
+        B, S = ogm.shape[0], self.cfg["input_size"][0]
+        lib = L.lib()
+        ws, n = self._workspace(self.workspace_bytes(B))
+        L.check(lib.sj_strajnet_fwd(ogm.data_ptr(), map_img.data_ptr(), flow.data_ptr(), obs.data_ptr(), occ.data_ptr(),
+                                    out.data_ptr(), C.byref(self.packed()), B, S, self.sj_dtype, ws, n, _stream()),
+                "STrajNet")
+        return out
+
+    def call(self, ogm, map_img, training=True, obs=None, occ=None, mapt=None, flow=None, dense_vec=None, dense_map=None):
+        _inference_only(training)
+        if obs is None or occ is None or flow is None:
+            raise ValueError("STrajNet: obs, occ and flow are required")
+        S = self.cfg["input_size"][0]
+        ogm = self._f32(ogm, (S, S, 11, 2))
+        map_img = self._f32(map_img, (256, 256, 3))
+        flow = self._f32(flow, (S, S, 2))
+        obs = self._f32(obs, (48, 11, 8))
+        occ = self._f32(occ, (16, 11, 8))  # mapt is ignored (actor_only=True, modules.py:778)
+        out = torch.empty(ogm.shape[0], 256, 256, 32, dtype=torch.float32, device=self.device)
+        return self.forward_into(out, ogm, map_img, obs, occ, flow)
