@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the occupancy-flow forward path (BASELINE.json metric: frames/sec @ 256x256x8, batch 16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32] [--batch 16]
+
+One "step" = one forward of STrajNet (cfg256, fg_msa=True, fg=True) over one batch of synthetic inputs
+per GPU.  N > 1 is launched by torchrun, one rank per GPU; batches shard data-parallel (weak scaling,
+16 frames per rank) with a single NCCL all-gather on the output grids per step (BASELINE config 4).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG256 = dict(input_size=(256, 256), window_size=8, embed_dim=96, depths=[2, 2, 2], num_heads=[3, 6, 12])
+GFLOP_PER_FRAME = 200.75          # nominal, reference formulation, cfg256 + FG-MSA
+METRIC = "occupancy_flow_frames_per_sec"
+UNIT = "frames/s"
+# nominal FLOPs of the dominant kernel per frame: upconv 96->48 @256^2 x 8 waypoints, ONE of the two heads
+PROBE_ROLE = "dec.upconv3"
+PROBE_GFLOP_PER_FRAME = 2 * 8 * 65536 * 9 * 96 * 48 / 1e9
+
+
+def synth_inputs(B, S=256, seed=0):
+    """Synthetic inputs with the value ranges of the reference's record decode (inference.py:84-96)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ogm = (rng.random((B, S, S, 11, 2), dtype=np.float32) < 0.03).astype(np.float32)
+    map_img = rng.integers(-128, 128, size=(B, 256, 256, 3)).astype(np.float32) / 256.0
+    flow = ((rng.random((B, S, S, 2), dtype=np.float32) < 0.03) * rng.uniform(-20, 20, size=(B, S, S, 2))).astype(np.float32)
+
+    def actors(n_max, lo):
+        a = np.zeros((B, n_max, 11, 8), np.float32)
+        for b in range(B):
+            for i in range(int(rng.integers(lo, n_max + 1))):
+                st = int(rng.integers(1, 12))
+                xy = rng.uniform(-80, 80, size=(st, 2))
+                xy[xy == 0] = 1.0
+                a[b, i, 11 - st:, 0:2] = xy
+                a[b, i, 11 - st:, 2:4] = rng.normal(0, 5, size=(st, 2))
+                a[b, i, 11 - st:, 4] = rng.uniform(-np.pi, np.pi, size=st)
+                a[b, i, :, 5 + int(rng.integers(0, 3))] = 1.0
+        return a
+
+    d = dict(ogm=ogm, map_img=map_img, flow=flow, obs=actors(48, 4), occ=actors(16, 0))
+    return {k: torch.from_numpy(v) for k, v in d.items()}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_fps(batch, iters, warmup=1):
+    """The CPU restatement of the reference graph (oracle/), fp32, all host threads."""
+    from oracle import strajnet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = O.make_weights(O.CFG256, seed=0)
+    inp = O.make_inputs(batch, 256, seed=0)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.forward_from_inputs(w, O.CFG256, inp)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            O.forward_from_inputs(w, O.CFG256, inp)
+        dt = time.perf_counter() - t0
+    return batch * iters / dt, cores, dt / iters
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  TensorFlow is not installable here
+    (SURVEY §8c), so this is the oracle port (kind "port"), on all host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    batch = 1
+    fps, cores, s_per_step = cpu_oracle_fps(batch, args.steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "STrajNet cfg256 fg_msa+fg forward, 256x256x8 grids (config 3 geometry)",
+                   "sample": f"batch {batch} per step on CPU (bounded sample of the batch-16 workload)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forwards of batch {batch}, torch-CPU fp32 oracle (not TF: not installable)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import strajnet_b200 as sj
+    from strajnet_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    B = args.batch
+    dtype = "bfloat16" if args.dtype == "bf16" else "float32"
+
+    model = sj.STrajNet(CFG256, fg_msa=True, fg=True, large_ogm=False, dtype=dtype, device=dev)
+    model.build()  # random-init weights of the reference architecture (Keras default initialisers, seeded)
+    host = {k: v.pin_memory() for k, v in synth_inputs(B, 256, seed=rank).items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    out = torch.empty(B, 256, 256, 32, dtype=torch.float32, device=dev)
+    gathered = torch.empty(world * B, 256, 256, 32, dtype=torch.float32, device=dev) if world > 1 else None
+    host_out = torch.empty(B, 256, 256, 32, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        model.forward_into(out, devin["ogm"], devin["map_img"], devin["obs"], devin["occ"], devin["flow"])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}  # pinned host -> device, every step
+        y = model(d["ogm"], d["map_img"], training=False, obs=d["obs"], occ=d["occ"], flow=d["flow"])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        host_out.copy_(y, non_blocking=True)  # device -> pinned host, every step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    lib.sj_launch_count(1)
+    step_resident()
+    launches_per_step = lib.sj_launch_count(1)
+
+    with ClockSampler(local) as clocks:
+        lib.sj_probe_start(PROBE_ROLE.encode())
+        ms = timed(step_resident, args.steps)
+        import ctypes
+        pms, pn = ctypes.c_double(0), ctypes.c_int(0)
+        lib.sj_probe_stop(ctypes.byref(pms), ctypes.byref(pn))
+    fps = world * B * args.steps / (ms / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    fps_e2e = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = host_out.numel() * host_out.element_size()
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # the kernel is timed inside a long step
+        roof = None
+        if pn.value > 0:
+            per_launch_ms = pms.value / pn.value
+            ach = PROBE_GFLOP_PER_FRAME * B / per_launch_ms  # GFLOP / ms = TFLOP/s
+            roof = {"bound": "tensor", "kernel": PROBE_ROLE, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src + ", sustained bf16",
+                    "launch_ms": per_launch_ms, "launches_timed": pn.value,
+                    "algorithmic_gflop_per_launch": PROBE_GFLOP_PER_FRAME * B,
+                    "forward_nominal_tflops": fps / world * GFLOP_PER_FRAME / 1e3,
+                    "forward_nominal_frac": fps / world * GFLOP_PER_FRAME / 1e3 / peak_tf}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cfps, cores, sps = cpu_oracle_fps(2, 4, 1)
+            cpu = {"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "4 forwards of batch 2 (after 1 warm-up), torch-CPU fp32 restatement of the reference graph "
+                             "(oracle/); TensorFlow is not installable here"}
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "STrajNet cfg256 (window 8, dims 96/192/384, depths 2/2/2) fg_msa+fg forward -> "
+                                   "[B,256,256,32], 8 waypoints, BASELINE config 3" + (" / config 4 sharding" if world > 1 else ""),
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "weights": "random init (Keras default initialisers)",
+                       "l2": "per-step inputs (113 MB) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush",
+                       "collective": "one NCCL all-gather of the fp32 output grids per step" if world > 1 else "none"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,13 @@ const char* sj_last_cuda_error(void); /* text of the last CUDA failure seen by t
 /* number of kernels launched by this thread through the library since the last reset */
 long long sj_launch_count(int reset);
 
+/* Opt-in timing probe for bench.py: CUDA events (created lazily by the library; the one exception to
+ * "allocates nothing") are recorded on the launching stream around every kernel launched by this thread
+ * whose forward step name starts with `role_prefix` ("enc", "fgmsa", "traj", "dec.upconv3", ...).
+ * sj_probe_stop synchronises on those events and returns their summed duration and count. */
+int sj_probe_start(const char* role_prefix);
+int sj_probe_stop(double* total_ms, int* n_launches);
+
 /* ---- integer maps (bit-exact rows of SURVEY §8 a3/a4/a5) --------------------------------- */
 /* WindowAttention.build, modules.py:88-100: int64 [ws*ws, ws*ws] */
 int sj_relative_position_index(int ws, int64_t* out, sj_stream_t stream);

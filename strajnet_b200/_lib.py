@@ -84,6 +84,8 @@ SIGNATURES = {
     "sj_strerror": (C.c_char_p, [_i]),
     "sj_last_cuda_error": (C.c_char_p, []),
     "sj_launch_count": (_ll, [_i]),
+    "sj_probe_start": (_i, [C.c_char_p]),
+    "sj_probe_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sj_relative_position_index": (_i, [_i, _p, _p]),
     "sj_shift_attn_mask": (_i, [_i, _i, _i, _i, _p, _p]),
     "sj_window_token_map": (_i, [_i, _i, _i, _i, _p, _p]),

@@ -21,6 +21,25 @@ void note_launch(Ctx& c, const char* what) {
   }
 }
 
+int probe_before(Ctx& c) {
+  TlsState& t = tls();
+  if (!t.probe_on || t.probe_n >= TlsState::kMaxProbe) return -1;
+  if (strncmp(c.role, t.probe_role, strlen(t.probe_role)) != 0) return -1;
+  int slot = t.probe_n++;
+  cudaEventRecord(t.probe_ev[2 * slot], c.stream);
+  return slot;
+}
+void probe_after(Ctx& c, int slot) {
+  if (slot >= 0) cudaEventRecord(tls().probe_ev[2 * slot + 1], c.stream);
+}
+
+struct RoleScope {
+  Ctx& c;
+  const char* prev;
+  RoleScope(Ctx& ctx, const char* r) : c(ctx), prev(ctx.role) { c.role = r; }
+  ~RoleScope() { c.role = prev; }
+};
+
 namespace {
 
 inline const void* adv(const Ctx& c, const void* p, long long elems) {
@@ -348,18 +367,19 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
   void* fx = c.alloc_act((size_t)NB * 64 * 64 * 128);
   void* x3 = c.alloc_act((size_t)NB * 128 * 128 * 96);
   void* x4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
-  upconv(c, x, x1, w.upconv[0], NB, 16, 384, 192);
-  res_add(c, res1, w.res[0], x1, x1, B, 32 * 32, 192, 192);
-  upconv(c, x1, x2, w.upconv[1], NB, 32, 192, 128);
-  res_add(c, res0, w.res[1], x2, x2, B, 64 * 64, 96, 128);
-  res_add(c, flow_res, w.res_f, x2, fx, B, 64 * 64, 96, 128);  // uses x AFTER the res0 add (modules.py:762-765)
-  upconv(c, x2, x3, w.upconv[2], NB, 64, 128, 96);
-  upconv(c, x3, x4, w.upconv[3], NB, 128, 96, 48);
+  { RoleScope r(c, "dec.upconv0"); upconv(c, x, x1, w.upconv[0], NB, 16, 384, 192); }
+  { RoleScope r(c, "dec.res0"); res_add(c, res1, w.res[0], x1, x1, B, 32 * 32, 192, 192); }
+  { RoleScope r(c, "dec.upconv1"); upconv(c, x1, x2, w.upconv[1], NB, 32, 192, 128); }
+  { RoleScope r(c, "dec.res1"); res_add(c, res0, w.res[1], x2, x2, B, 64 * 64, 96, 128); }
+  // uses x AFTER the res0 add (modules.py:762-765)
+  { RoleScope r(c, "dec.resf"); res_add(c, flow_res, w.res_f, x2, fx, B, 64 * 64, 96, 128); }
+  { RoleScope r(c, "dec.upconv2"); upconv(c, x2, x3, w.upconv[2], NB, 64, 128, 96); }
+  { RoleScope r(c, "dec.upconv3"); upconv(c, x3, x4, w.upconv[3], NB, 128, 96, 48); }
   void* f3 = x3;  // x3 is dead once x4 exists
-  upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96);
+  { RoleScope r(c, "dec.upconvf0"); upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96); }
   void* f4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
-  upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48);
-  out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out);
+  { RoleScope r(c, "dec.upconvf1"); upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48); }
+  { RoleScope r(c, "dec.outconv"); out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out); }
   c.ws.release(mark);
 }
 
@@ -373,19 +393,20 @@ void strajnet_impl(Ctx& c, const float* ogm, const float* map_img, const float* 
   void* res2 = c.alloc_act((size_t)B * 256 * 384);
   void* query = c.alloc_act((size_t)B * 2048 * 384);
   void* obs_value = c.alloc_act((size_t)B * 2048 * 384);
-  encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm);
+  { RoleScope r(c, "enc"); encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm); }
   const void* q2 = res2;
   float* off = nullptr;
   if (w.fg_msa) {
     void* q2b = c.alloc_act((size_t)B * 256 * 384);
     off = (float*)c.alloc((size_t)B * 4096 * 2 * 4);
     float* pos = (float*)c.alloc((size_t)B * 4096 * 2 * 4);
+    RoleScope r(c, "fgmsa");
     fgmsa_impl(c, res2, q2b, off, pos, w.fgmsa, B, true);  // q = res + q (modules.py:825)
     q2 = q2b;
   }
   if (w.fg && !w.fg_msa) { c.fail(SJ_EINVAL); return; }
   build_query(c, q2, off, &w.fgmsa, B, w.fg, query);  // repeat x8 (+ flow_hidden), modules.py:827-831
-  traj_impl(c, query, obs, occ, obs_value, w.traj, B);
+  { RoleScope r(c, "traj"); traj_impl(c, query, obs, occ, obs_value, w.traj, B); }
   decoder_impl(c, obs_value, flow_res, res0, res1, out, w.decoder, B, 1);
   c.ws.release(mark);
 }
@@ -465,6 +486,36 @@ const char* sj_strerror(int status) {
 }
 
 const char* sj_last_cuda_error(void) { return tls().cuda_err; }
+
+int sj_probe_start(const char* role_prefix) {
+  TlsState& t = tls();
+  if (!role_prefix || strlen(role_prefix) >= sizeof(t.probe_role)) return SJ_EINVAL;
+  if (!t.probe_ev_ready) {
+    for (int i = 0; i < 2 * TlsState::kMaxProbe; ++i)
+      if (cudaEventCreate(&t.probe_ev[i]) != cudaSuccess) return SJ_ECUDA;
+    t.probe_ev_ready = true;
+  }
+  strcpy(t.probe_role, role_prefix);
+  t.probe_n = 0;
+  t.probe_on = true;
+  return SJ_OK;
+}
+
+int sj_probe_stop(double* total_ms, int* n_launches) {
+  TlsState& t = tls();
+  t.probe_on = false;
+  double tot = 0.0;
+  for (int i = 0; i < t.probe_n; ++i) {
+    if (cudaEventSynchronize(t.probe_ev[2 * i + 1]) != cudaSuccess) return SJ_ECUDA;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.probe_ev[2 * i], t.probe_ev[2 * i + 1]) != cudaSuccess) return SJ_ECUDA;
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = t.probe_n;
+  t.probe_n = 0;
+  return SJ_OK;
+}
 
 long long sj_launch_count(int reset) {
   long long n = tls().launches;

@@ -14,6 +14,14 @@ typedef __nv_bfloat16 bf16;
 struct TlsState {
   long long launches = 0;
   char cuda_err[256] = {0};
+  // opt-in timing probe (sj_probe_start / sj_probe_stop): CUDA events around every launch whose
+  // role starts with `probe_role`, recorded on the launching stream
+  static constexpr int kMaxProbe = 1024;
+  bool probe_on = false;
+  char probe_role[64] = {0};
+  int probe_n = 0;
+  cudaEvent_t probe_ev[2 * kMaxProbe] = {};
+  bool probe_ev_ready = false;
 };
 TlsState& tls();
 
@@ -40,6 +48,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int dtype = SJ_F32;
   bool dry = false;  // dry run: only size the workspace, launch nothing
+  const char* role = "";  // which step of the forward is being enqueued (for the timing probe)
   Arena ws;
   int status = SJ_OK;
   size_t esize() const { return dtype == SJ_BF16 ? 2 : 4; }
@@ -54,11 +63,16 @@ struct Ctx {
 
 // records a launch, and the CUDA error if one is pending
 void note_launch(Ctx& c, const char* what);
+// timing probe hooks around a launch (no-ops unless a probe is armed and the role matches)
+int probe_before(Ctx& c);
+void probe_after(Ctx& c, int slot);
 
 #define SJ_LAUNCH(ctx, what, kernel, grid, block, smem, ...)                 \
   do {                                                                      \
     if (!(ctx).dry && (ctx).ok()) {                                         \
+      int sj_slot_ = sj::probe_before(ctx);                                 \
       kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);       \
+      sj::probe_after((ctx), sj_slot_);                                     \
       sj::note_launch((ctx), what);                                         \
     }                                                                       \
   } while (0)

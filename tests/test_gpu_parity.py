@@ -1,0 +1,287 @@
+"""GPU parity tests: every layer of the CUDA path (through the C ABI, via the Python mirror of the
+reference's Keras classes) against the CPU oracle on the same seeded inputs.
+
+Tolerances: bit-exact for integer / index maps; <= 1e-3 abs for fp32 (north_star); bf16 is reported
+and gated loosely (it is not the parity configuration).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import strajnet_oracle as O
+from tests.util import max_abs, oracle_model, randn, sub
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3
+CFG256 = O.CFG256
+
+
+@pytest.fixture(scope="module")
+def sj():
+    import strajnet_b200
+    assert torch.cuda.is_available()
+    return strajnet_b200
+
+
+# ------------------------------------------------------------------------------------ integer maps
+def test_relative_position_index_bit_exact(sj, golden_dir):
+    g = np.load(f"{golden_dir}/ref_index_maps.npz")
+    out = sj.relative_position_index(8).cpu().numpy()
+    assert out.dtype == np.int64
+    assert np.array_equal(out, g["relative_position_index_ws8"])
+
+
+@pytest.mark.parametrize("H", [16, 32, 64, 128])
+def test_shift_mask_bit_exact(sj, golden_dir, H):
+    g = np.load(f"{golden_dir}/ref_index_maps.npz")
+    out = sj.shift_attn_mask(H, H, 8, 4).cpu().numpy()
+    assert np.array_equal(out, g[f"shift_mask_{H}"].astype(np.float32))
+
+
+@pytest.mark.parametrize("H,W,shift", [(16, 16, 0), (16, 16, 4), (64, 64, 4), (32, 64, 4), (128, 128, 0)])
+def test_window_token_map_bit_exact(sj, H, W, shift):
+    idx = torch.arange(H * W, dtype=torch.float32).reshape(1, H, W, 1)
+    if shift:
+        idx = torch.roll(idx, (-shift, -shift), (1, 2))
+    ref = O.window_partition(idx, 8).reshape(-1).to(torch.int32)
+    out = sj.window_token_map(H, W, 8, shift).cpu()
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_partition_reverse_bit_exact(sj, dtype):
+    x = randn((3, 16, 24, 32), 1).to(dtype)
+    w = sj.window_partition(x.cuda(), 8)
+    assert torch.equal(w.cpu(), O.window_partition(x, 8))
+    back = sj.window_reverse(w, 8, 16, 24, 32)
+    assert torch.equal(back.cpu(), x)
+
+
+# ------------------------------------------------------------------------------------ Swin pieces
+def test_mlp(sj):
+    w = O.make_block_weights(96, 3, seed=5)
+    m = sj.Mlp(96, 384)
+    m.set_weights(sub(w, "mlp."))
+    x = randn((2, 100, 96), 6)
+    ref = O.dense(O.gelu_tanh(O.dense(x, w["mlp.fc1.kernel"], w["mlp.fc1.bias"])), w["mlp.fc2.kernel"], w["mlp.fc2.bias"])
+    assert max_abs(m(x), ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("C,heads,masked", [(32, 2, False), (32, 1, True), (96, 3, True), (384, 12, False)])
+def test_window_attention(sj, C, heads, masked):
+    w = O.make_block_weights(C, heads, seed=7)
+    layer = sj.WindowAttention(C, (8, 8), heads)
+    layer.set_weights(sub(w, "attn."))
+    nW = 4
+    x = randn((2 * nW, 64, C), 8)
+    mask = torch.from_numpy(O.shift_attn_mask(16, 16, 8, 4)).float() if masked else None
+    ref = O.window_attention(x, w, "attn.", heads, 8, mask)
+    assert max_abs(layer(x, mask=mask), ref) < FP32_TOL
+    assert torch.equal(layer.relative_position_index.cpu(), torch.from_numpy(O.relative_position_index(8)))
+
+
+@pytest.mark.parametrize("heads", [1, 2])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_swin_block_config1(sj, golden_dir, heads, shift):
+    """BASELINE config 1: SwinTransformerBlock(dim=32, (64,64), window 8), batch 1."""
+    w = O.make_block_weights(32, heads, seed=0)
+    blk = sj.SwinTransformerBlock(32, (64, 64), heads, window_size=8, shift_size=shift)
+    blk.set_weights(w)
+    x = randn((1, 4096, 32), 0)
+    y = blk(x)
+    ref = O.swin_block(x, w, "", 64, 64, heads, 8, shift)
+    assert max_abs(y, ref) < FP32_TOL
+    g = np.load(f"{golden_dir}/oracle_outputs.npz")[f"block_c32_h{heads}_s{shift}"]
+    assert np.abs(y[0, ::37].cpu().numpy() - g).max() < FP32_TOL
+    if shift:
+        assert torch.equal(blk.attn_mask.cpu(), torch.from_numpy(O.shift_attn_mask(64, 64, 8, 4)).float())
+
+
+@pytest.mark.parametrize("C,heads,H,B", [(96, 3, 64, 2), (192, 6, 32, 2), (384, 12, 16, 3), (96, 3, 8, 1)])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_swin_block_model_shapes(sj, C, heads, H, B, shift):
+    w = O.make_block_weights(C, heads, seed=11)
+    blk = sj.SwinTransformerBlock(C, (H, H), heads, window_size=8, shift_size=shift)
+    blk.set_weights(w)
+    x = randn((B, H * H, C), 12)
+    ref = O.swin_block(x, w, "", H, H, heads, 8, shift)
+    assert max_abs(blk(x), ref) < FP32_TOL
+
+
+def test_swin_block_rejects_wrong_length(sj):
+    blk = sj.SwinTransformerBlock(32, (64, 64), 2, window_size=8)
+    with pytest.raises(AssertionError):
+        blk(randn((1, 4000, 32)))
+
+
+def test_patch_merging(sj):
+    w = oracle_model()
+    p = "encoder.basic_layers.0.downsample."
+    layer = sj.PatchMerging((64, 64), 96)
+    layer.set_weights(sub(w, p))
+    x = randn((2, 4096, 96), 13)
+    assert max_abs(layer(x), O.patch_merging(x, w, p, 64, 64)) < FP32_TOL
+
+
+@pytest.mark.parametrize("name,cin", [("vecicle", 11), ("map", 3), ("flow", 2)])
+def test_patch_embed(sj, name, cin):
+    w = oracle_model()
+    p = f"encoder.patch_embed_{name}."
+    layer = sj.PatchEmbed((256, 256), (4, 4), cin, 96)
+    layer.set_weights(sub(w, p))
+    x = randn((2, 256, 256, cin), 14)
+    assert max_abs(layer(x), O.patch_embed(x, w, p)) < FP32_TOL
+
+
+def test_basic_layer(sj):
+    w = oracle_model()
+    p = "encoder.basic_layers.1."
+    layer = sj.BasicLayer(192, (32, 32), 2, 6, 8, downsample=True)
+    layer.set_weights(sub(w, p))
+    x = randn((2, 1024, 192), 15)
+    yd, res = layer(x)
+    rd, rres = O.basic_layer(x, w, p, 32, 32, 2, 6, 8, True)
+    assert max_abs(res, rres) < FP32_TOL and max_abs(yd, rd) < FP32_TOL
+
+
+@pytest.mark.parametrize("S,large", [(256, False), (512, True)])
+def test_encoder(sj, S, large):
+    cfg = O.CFG512 if large else O.CFG256
+    w = oracle_model()
+    enc = sj.SwinTransformerEncoder(img_size=cfg["input_size"], window_size=8, embed_dim=96, depths=[2, 2, 2],
+                                    num_heads=[3, 6, 12], sep_encode=True, flow_sep=True, use_flow=True, large_input=large)
+    enc.set_weights(sub(w, "encoder."))
+    inp = O.make_inputs(1, S, seed=2)
+    outs = enc(inp["ogm"], inp["map_img"], inp["flow"], training=False)
+    refs = O.encoder_forward(inp["ogm"], inp["map_img"], inp["flow"], w, cfg, large)
+    for o, r in zip(outs, refs):
+        assert tuple(o.shape) == tuple(r.shape)
+        assert max_abs(o, r) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------ FG-MSA, trajectories, decoder
+def test_fgmsa(sj):
+    w = oracle_model()
+    layer = sj.FGMSA((16, 16), (16, 16), 8, 48, n_groups=8, out_dim=384, fg=True)
+    layer.set_weights(sub(w, "fg_msa_layer."))
+    x = randn((2, 16, 16, 384), 16)
+    y, pos, hid = layer(x, training=False)
+    ry, rpos, rhid = O.fgmsa_forward(x, w)
+    assert max_abs(pos, rpos) < FP32_TOL
+    assert max_abs(hid, rhid) < FP32_TOL
+    assert max_abs(y, ry) < FP32_TOL
+
+
+def _traj_inputs(B, seed, mode="normal"):
+    inp = O.make_inputs(B, 256, seed=seed)
+    obs, occ = inp["obs"], inp["occ"]
+    if mode == "no_occ":
+        occ = torch.zeros_like(occ)
+    elif mode == "all_padded":  # every actor padded: all attention rows fully masked -> uniform (Q7)
+        obs, occ = torch.zeros_like(obs), torch.zeros_like(occ)
+    return obs, occ
+
+
+@pytest.mark.parametrize("mode", ["normal", "no_occ", "all_padded"])
+def test_traj_cross_attention(sj, mode):
+    w = oracle_model()
+    layer = sj.TrajNetCrossAttention(dict(traj_heads=4, att_heads=6, out_dim=384, no_attn=False), pic_size=(16, 16), pic_dim=384)
+    layer.set_weights(sub(w, "trajnet_attn."))
+    B = 2
+    pic = randn((B, 8, 16, 16, 384), 17)
+    obs, occ = _traj_inputs(B, 3, mode)
+    out = layer(pic, obs, occ, None, training=False)
+    ref = O.trajnet_cross_attention(pic, obs, occ, w)
+    assert max_abs(out, ref) < FP32_TOL
+
+
+def test_decoder(sj):
+    w = oracle_model()
+    dec = sj.Pyramid3DDecoder(None, (256, 256), use_pyramid=True, timestep_split=True, shallow_decode=1,
+                              flow_sep_decode=True, conv_cnn=False)
+    dec.set_weights(sub(w, "decoder."))
+    B = 1
+    x = randn((B, 8, 16, 16, 384), 18)
+    res = [randn((B, 4096, 96), 19), randn((B, 4096, 96), 20), randn((B, 1024, 192), 21), randn((B, 16, 16, 384), 22)]
+    out = dec(x, training=False, res_list=res)
+    ref = O.decoder_forward(x, res, w)
+    assert tuple(out.shape) == (B, 8, 256, 256, 4)
+    assert max_abs(out, ref) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------ whole forward
+def _model(sj, fg_msa=True, fg=True, large=False, dtype="float32"):
+    cfg = O.CFG512 if large else O.CFG256
+    m = sj.STrajNet(cfg, fg_msa=fg_msa, fg=fg, large_ogm=large, dtype=dtype)
+    m.set_weights(oracle_model(fg_msa=fg_msa, fg=fg))
+    return m
+
+
+def _fwd(m, inp):
+    return m(inp["ogm"], inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], mapt=inp["mapt"], flow=inp["flow"])
+
+
+def test_strajnet_config2_fp32(sj, golden_dir):
+    """BASELINE config 2: full forward, 256x256, 8 waypoints, batch 1, fp32, <= 1e-3 abs vs the oracle."""
+    m = _model(sj)
+    inp = O.make_inputs(1, 256, seed=0)
+    y = _fwd(m, inp)
+    assert tuple(y.shape) == (1, 256, 256, 32) and y.dtype == torch.float32
+    ref = O.forward_from_inputs(oracle_model(), CFG256, inp)
+    err = max_abs(y, ref)
+    print(f"config2 fp32 max abs err vs oracle: {err:.3e}")
+    assert err < FP32_TOL
+    g = np.load(f"{golden_dir}/oracle_outputs.npz")["forward_cfg256_fg"]
+    assert np.abs(y[0, ::16, ::16].cpu().numpy() - g).max() < FP32_TOL
+
+
+def test_strajnet_without_fgmsa(sj):
+    m = _model(sj, fg_msa=False, fg=False)
+    inp = O.make_inputs(1, 256, seed=4)
+    ref = O.forward_from_inputs(oracle_model(fg_msa=False, fg=False), CFG256, inp, fg_msa=False, fg=False)
+    assert max_abs(_fwd(m, inp), ref) < FP32_TOL
+
+
+def test_strajnet_batch_invariance_and_parity_b3(sj):
+    m = _model(sj)
+    inp = O.make_inputs(3, 256, seed=5)
+    y = _fwd(m, inp)
+    ref = O.forward_from_inputs(oracle_model(), CFG256, inp)
+    assert max_abs(y, ref) < FP32_TOL
+    one = {k: v[1:2] for k, v in inp.items()}
+    assert torch.equal(_fwd(m, one)[0], y[1])  # sample i of a batch == the batch-1 result, bit for bit
+
+
+def test_strajnet_config5_large_input(sj):
+    """BASELINE config 5 geometry (512x512 input, large_ogm=True) at batch 1."""
+    m = _model(sj, large=True)
+    inp = O.make_inputs(1, 512, seed=6)
+    ref = O.forward_from_inputs(oracle_model(), O.CFG512, inp, large_ogm=True)
+    assert max_abs(_fwd(m, inp), ref) < FP32_TOL
+
+
+def test_strajnet_bf16_reported(sj):
+    """BASELINE config 3 arithmetic (bf16 activations, fp32 accumulate): error reported, gated loosely."""
+    m = _model(sj, dtype="bfloat16")
+    inp = O.make_inputs(2, 256, seed=7)
+    y = _fwd(m, inp)
+    ref = O.forward_from_inputs(oracle_model(), CFG256, inp)
+    err = max_abs(y, ref)
+    rel = err / ref.abs().max().item()
+    print(f"bf16 max abs err vs fp32 oracle: {err:.3e} (rel to max |y|: {rel:.3e})")
+    assert torch.isfinite(y).all() and rel < 0.08
+
+
+def test_empty_and_bad_inputs(sj):
+    m = _model(sj)
+    inp = O.make_inputs(1, 256, seed=0)
+    with pytest.raises(ValueError):
+        m(inp["ogm"][:, :128], inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
+    with pytest.raises(ValueError):
+        m(inp["ogm"], inp["map_img"], training=False, obs=inp["obs"][:, :10], occ=inp["occ"], flow=inp["flow"])
+    with pytest.raises(NotImplementedError):
+        m(inp["ogm"], inp["map_img"], obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])  # training defaults to True
+    z = {k: torch.zeros_like(v) for k, v in inp.items()}  # the reference's own dummy-zero build call
+    ref = O.forward_from_inputs(oracle_model(), CFG256, z)
+    assert max_abs(_fwd(m, z), ref) < FP32_TOL
