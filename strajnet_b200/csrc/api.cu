@@ -417,6 +417,8 @@ size_t measure(int dtype, F&& body) {
   Ctx d;
   d.dry = true;
   d.dtype = dtype;
+  d.ws.base = (char*)4096;  // fake, never dereferenced: dry runs launch nothing
+  d.ws.cap = ~size_t(0) >> 2;
   body(d);
   return d.ws.high + 256;
 }
@@ -427,6 +429,8 @@ int run(void* ws, size_t ws_bytes, int dtype, sj_stream_t stream, F&& body) {
   Ctx d;
   d.dry = true;
   d.dtype = dtype;
+  d.ws.base = (char*)4096;  // fake, never dereferenced: dry runs launch nothing
+  d.ws.cap = ~size_t(0) >> 2;
   body(d);
   if (d.status != SJ_OK) return d.status;
   if (d.ws.high > 0) {

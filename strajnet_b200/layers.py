@@ -66,7 +66,6 @@ class Layer:
             new[k] = t
         self.weights = new
         self._packed = None
-        self.built = True
 
     def get_weights(self) -> Dict[str, Tensor]:
         if not self.built:
