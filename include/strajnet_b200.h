@@ -43,8 +43,11 @@ typedef enum {
 } SjStatus;
 
 /* Dense / conv weights.  w: fp32 [K,N] (Keras [in,out], conv taps flattened into K);
- * b: fp32 [N] or NULL; w_tc: bf16 [N,K] (K-major) tensor-core copy or NULL.          */
-typedef struct { const float* w; const float* b; const void* w_tc; } SjLinear;
+ * b: fp32 [N] or NULL; w_tc: bf16 [N,K] (K-major) tensor-core copy or NULL.
+ * When the layer consumes a LayerNorm output, the tensor-core copy has the norm folded in:
+ * w_tc = bf16(gamma[k]*w[k,n]), tc_colsum[n] = sum_k w_tc[n,k], tc_bias[n] = b[n] + sum_k beta[k]*w[k,n];
+ * the kernel then applies  rstd*(x.w_tc - mean*tc_colsum) + tc_bias  in its epilogue (else both NULL). */
+typedef struct { const float* w; const float* b; const void* w_tc; const float* tc_colsum; const float* tc_bias; } SjLinear;
 typedef struct { const float* g; const float* b; } SjNorm; /* LayerNormalization gamma/beta */
 
 /* SwinTransformerBlock (modules.py:163-262) incl. WindowAttention (:66-134) and Mlp (:31-46). */
@@ -151,6 +154,8 @@ const char* sj_strerror(int status);
 const char* sj_last_cuda_error(void); /* text of the last CUDA failure seen by this thread */
 /* number of kernels launched by this thread through the library since the last reset */
 long long sj_launch_count(int reset);
+/* of which tcgen05 (tensor-core) kernels */
+long long sj_tc_launch_count(int reset);
 
 /* Opt-in timing probe for bench.py: CUDA events (created lazily by the library; the one exception to
  * "allocates nothing") are recorded on the launching stream around every kernel launched by this thread
@@ -172,6 +177,10 @@ int sj_window_partition_fwd(const void* x, void* windows, int B, int H, int W, i
 int sj_window_reverse_fwd(const void* windows, void* x, int B, int H, int W, int C, int ws, int dtype, sj_stream_t stream);
 
 /* ---- layers ------------------------------------------------------------------------------ */
+/* keras.layers.Dense(units=N, activation=act) as used throughout modules.py / trajNet.py: y = act(x[M,K] . w + b);
+ * act 0 none, 1 tanh-GELU (modules.py:18), 2 ELU */
+int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K, int act, int dtype, sj_stream_t stream);
+
 /* Mlp.call, modules.py:40-46: y = fc2(Gelu(fc1(x))), x [M,C] */
 size_t sj_mlp_workspace_bytes(int M, int C, int hidden, int dtype);
 int sj_mlp_fwd(const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2, int M, int C, int hidden,

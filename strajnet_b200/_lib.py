@@ -19,7 +19,7 @@ c_fp = C.c_void_p  # device pointers travel as plain addresses
 
 
 class SjLinear(C.Structure):
-    _fields_ = [("w", c_fp), ("b", c_fp), ("w_tc", c_fp)]
+    _fields_ = [("w", c_fp), ("b", c_fp), ("w_tc", c_fp), ("tc_colsum", c_fp), ("tc_bias", c_fp)]
 
 
 class SjNorm(C.Structure):
@@ -84,6 +84,7 @@ SIGNATURES = {
     "sj_strerror": (C.c_char_p, [_i]),
     "sj_last_cuda_error": (C.c_char_p, []),
     "sj_launch_count": (_ll, [_i]),
+    "sj_tc_launch_count": (_ll, [_i]),
     "sj_probe_start": (_i, [C.c_char_p]),
     "sj_probe_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sj_relative_position_index": (_i, [_i, _p, _p]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "sj_window_token_map": (_i, [_i, _i, _i, _i, _p, _p]),
     "sj_window_partition_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sj_window_reverse_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sj_dense_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
     "sj_mlp_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sj_mlp_fwd": (_i, [_p, _p, C.POINTER(SjLinear), C.POINTER(SjLinear), _i, _i, _i, _i, _p, _sz, _p]),
     "sj_window_attention_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -14,6 +14,7 @@ TlsState& tls() {
 
 void note_launch(Ctx& c, const char* what) {
   tls().launches++;
+  if (what[0] == 't' && what[1] == 'c' && what[2] == '_') tls().tc_launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(tls().cuda_err, sizeof(tls().cuda_err), "%s: %s", what, cudaGetErrorString(e));
@@ -50,7 +51,7 @@ inline const void* adv(const Ctx& c, const void* p, long long elems) {
 void linear(Ctx& c, const void* A, int lda, const SjLinear& w, void* C, int ldc, int M, int N, int K, int act,
             const void* R = nullptr, int ldr = 0) {
   GemmP g;
-  g.A = A; g.lda = lda; g.W = w.w; g.ldw = N; g.bias = w.b; g.C = C; g.ldc = ldc;
+  g.A = A; g.lda = lda; g.set_weights(w); g.ldw = N; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.act = act; g.R = R; g.ldr = ldr;
   gemm(c, g);
 }
@@ -76,10 +77,14 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   void* x1 = c.alloc_act(M * C);
   void* hbuf = c.alloc_act(M * 4 * C);
 
-  ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
-  {  // norm1 -> roll -> partition -> qkv   (modules.py:226-239, :105)
+  if (c.dtype == SJ_BF16) {
+    // tensor-core path: norm1 + roll + partition as one gather pass, then a plain GEMM
+    layernorm_gather(c, x, x1, (int)M, C, w.norm1.g, w.norm1.b, 1e-5f, map, L);
+    linear(c, x1, C, w.qkv, qkv, 3 * C, (int)M, 3 * C, C, ACT_NONE);
+  } else {  // norm1 -> roll -> partition -> qkv   (modules.py:226-239, :105)
+    ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
     GemmP g;
-    g.A = x; g.lda = C; g.W = w.qkv.w; g.ldw = 3 * C; g.bias = w.qkv.b; g.C = qkv; g.ldc = 3 * C;
+    g.A = x; g.lda = C; g.set_weights(w.qkv); g.ldw = 3 * C; g.C = qkv; g.ldc = 3 * C;
     g.M = (int)M; g.N = 3 * C; g.K = C;
     g.am.map = map; g.am.map_len = L;
     g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm1.g; g.ln_b = w.norm1.b;
@@ -88,7 +93,7 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   window_attn_core(c, qkv, o, w.rpb_table, (int)(M / 64), C, heads, shift > 0 ? 1 : 0, H, W, shift, nullptr, 0);
   {  // proj -> window_reverse -> roll back -> + shortcut   (modules.py:132, :245-258)
     GemmP g;
-    g.A = o; g.lda = C; g.W = w.proj.w; g.ldw = C; g.bias = w.proj.b; g.C = x1; g.ldc = C;
+    g.A = o; g.lda = C; g.set_weights(w.proj); g.ldw = C; g.C = x1; g.ldc = C;
     g.M = (int)M; g.N = C; g.K = C;
     g.cm.map = map; g.cm.map_len = L;
     g.R = x; g.ldr = C;
@@ -97,7 +102,7 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   ln_stats(c, x1, (int)M, C, C, 1e-5f, mean, rstd);
   {  // norm2 -> fc1 -> GELU   (modules.py:260, :41-42)
     GemmP g;
-    g.A = x1; g.lda = C; g.W = w.fc1.w; g.ldw = 4 * C; g.bias = w.fc1.b; g.C = hbuf; g.ldc = 4 * C;
+    g.A = x1; g.lda = C; g.set_weights(w.fc1); g.ldw = 4 * C; g.C = hbuf; g.ldc = 4 * C;
     g.M = (int)M; g.N = 4 * C; g.K = C; g.act = ACT_GELU;
     g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
     gemm(c, g);
@@ -117,7 +122,7 @@ void patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, 
   ln_stats_merge(c, x, B, H, W, C, 1e-5f, mean, rstd);
   GemmP g;
   g.amode = A_MERGE; g.A = x; g.H = H; g.Wd = W; g.Cin = C;
-  g.W = w.reduction.w; g.ldw = 2 * C; g.C = y; g.ldc = 2 * C; g.M = M; g.N = 2 * C; g.K = 4 * C;
+  g.set_weights(w.reduction); g.ldw = 2 * C; g.C = y; g.ldc = 2 * C; g.M = M; g.N = 2 * C; g.K = 4 * C;
   g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm.g; g.ln_b = w.norm.b;
   g.R = add; g.ldr = 2 * C;
   gemm(c, g);
@@ -275,7 +280,7 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
   ln_stats(c, V0, NA, 384, 384, 1e-3f, mean, rstd);
   {
     GemmP g;
-    g.A = V0; g.lda = 384; g.W = w.ia_ffn1.w; g.ldw = 1536; g.bias = w.ia_ffn1.b; g.C = F1; g.ldc = 1536;
+    g.A = V0; g.lda = 384; g.set_weights(w.ia_ffn1); g.ldw = 1536; g.C = F1; g.ldc = 1536;
     g.M = NA; g.N = 1536; g.K = 384; g.act = ACT_ELU;
     g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.ia_norm1.g; g.ln_b = w.ia_norm1.b;
     gemm(c, g);
@@ -295,13 +300,13 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
   pm.inner = 256; pm.outer = 2048; pm.gstride = 256;
   {
     GemmP g;
-    g.A = pic; g.lda = 384; g.W = w.ca_q.w; g.ldw = 128; g.w_gstride = 384 * 128; g.C = Qc; g.ldc = 128;
+    g.A = pic; g.lda = 384; g.set_weights(w.ca_q); g.ldw = 128; g.w_gstride = 384 * 128; g.C = Qc; g.ldc = 128;
     g.M = MQ; g.N = 128; g.K = 384; g.groups = 8; g.am = pm; g.cm = pm;
     gemm(c, g);
   }
   {
     GemmP g;
-    g.A = key; g.lda = 384; g.W = w.ca_kv.w; g.ldw = 256; g.w_gstride = 384 * 256; g.C = KVc; g.ldc = 256;
+    g.A = key; g.lda = 384; g.set_weights(w.ca_kv); g.ldw = 256; g.w_gstride = 384 * 256; g.C = KVc; g.ldc = 256;
     g.M = NA; g.N = 256; g.K = 384; g.groups = 8;
     g.cm.inner = 64; g.cm.outer = 512; g.cm.gstride = 64;
     gemm(c, g);
@@ -316,14 +321,14 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
   }
   {
     GemmP g;
-    g.A = Oc; g.lda = 128; g.W = w.ca_proj.w; g.ldw = 128; g.w_gstride = 128 * 128; g.bias = w.ca_proj.b;
+    g.A = Oc; g.lda = 128; g.set_weights(w.ca_proj); g.ldw = 128; g.w_gstride = 128 * 128;
     g.bias_gstride = 128; g.C = P1; g.ldc = 128; g.M = MQ; g.N = 128; g.K = 128; g.groups = 8; g.am = pm; g.cm = pm;
     gemm(c, g);
   }
   ln_stats(c, P1, B * 2048, 128, 128, 1e-3f, mean, rstd);
   {
     GemmP g;
-    g.A = P1; g.lda = 128; g.W = w.ca_ffn1.w; g.ldw = 512; g.w_gstride = 128 * 512; g.bias = w.ca_ffn1.b;
+    g.A = P1; g.lda = 128; g.set_weights(w.ca_ffn1); g.ldw = 512; g.w_gstride = 128 * 512;
     g.bias_gstride = 512; g.C = Fc; g.ldc = 512; g.M = MQ; g.N = 512; g.K = 128; g.groups = 8; g.am = pm; g.cm = pm;
     g.act = ACT_ELU;
     g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.ca_norm1.g; g.ln_b = w.ca_norm1.b; g.ln_gstride = 128;
@@ -331,7 +336,7 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
   }
   {
     GemmP g;
-    g.A = Fc; g.lda = 512; g.W = w.ca_ffn2.w; g.ldw = 384; g.w_gstride = 512 * 384; g.bias = w.ca_ffn2.b;
+    g.A = Fc; g.lda = 512; g.set_weights(w.ca_ffn2); g.ldw = 384; g.w_gstride = 512 * 384;
     g.bias_gstride = 384; g.C = Gc; g.ldc = 384; g.M = MQ; g.N = 384; g.K = 512; g.groups = 8; g.am = pm; g.cm = pm;
     gemm(c, g);
   }
@@ -344,14 +349,14 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
 void upconv(Ctx& c, const void* x, void* y, const SjLinear& w, int NB, int Hin, int Cin, int Cout) {
   GemmP g;
   g.amode = A_CONV3; g.A = x; g.H = 2 * Hin; g.Wd = 2 * Hin; g.Cin = Cin; g.up = 1;
-  g.W = w.w; g.ldw = Cout; g.bias = w.b; g.C = y; g.ldc = Cout;
+  g.set_weights(w); g.ldw = Cout; g.C = y; g.ldc = Cout;
   g.M = NB * 4 * Hin * Hin; g.N = Cout; g.K = 9 * Cin; g.act = ACT_ELU;
   gemm(c, g);
 }
 // dst[b,t] = src[b,t] + ELU(skip[b] . W_eff[t] + bias): the collapsed (8,1,1) Conv3D
 void res_add(Ctx& c, const void* skip, const SjLinear& w, const void* src, void* dst, int B, int HW, int Cin, int Cout) {
   GemmP g;
-  g.A = skip; g.lda = Cin; g.W = w.w; g.ldw = Cout; g.w_gstride = (long long)Cin * Cout; g.bias = w.b;
+  g.A = skip; g.lda = Cin; g.set_weights(w); g.ldw = Cout; g.w_gstride = (long long)Cin * Cout;
   g.C = dst; g.ldc = Cout; g.R = src; g.ldr = Cout;
   g.M = B * HW; g.N = Cout; g.K = Cin; g.groups = 8; g.act = ACT_ELU;
   g.cm.inner = HW; g.cm.outer = 8 * HW; g.cm.gstride = HW;
@@ -527,6 +532,12 @@ long long sj_launch_count(int reset) {
   return n;
 }
 
+long long sj_tc_launch_count(int reset) {
+  long long n = tls().tc_launches;
+  if (reset) tls().tc_launches = 0;
+  return n;
+}
+
 int sj_relative_position_index(int ws, int64_t* out, sj_stream_t stream) {
   SJ_REQUIRE(out && ws > 0 && ws <= 16);
   return run(nullptr, 0, SJ_F32, stream, [&](Ctx& c) { relative_position_index(c, ws, out); });
@@ -568,6 +579,12 @@ int sj_mlp_fwd(const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2,
                void* workspace, size_t workspace_bytes, sj_stream_t stream) {
   SJ_REQUIRE(x && y && fc1 && fc2 && fc1->w && fc2->w && M > 0);
   return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { mlp_body(c, x, y, fc1, fc2, M, C, hidden); });
+}
+
+// ---- Dense ----
+int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K, int act, int dtype, sj_stream_t stream) {
+  SJ_REQUIRE(x && y && w && w->w && M > 0 && act >= 0 && act <= 2);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) { linear(c, x, K, *w, y, N, M, N, K, act); });
 }
 
 // ---- WindowAttention ----

@@ -13,6 +13,7 @@ typedef __nv_bfloat16 bf16;
 // ---- per-thread library state ---------------------------------------------------------------
 struct TlsState {
   long long launches = 0;
+  long long tc_launches = 0;  // launches of tcgen05 kernels (names starting with "tc_")
   char cuda_err[256] = {0};
   // opt-in timing probe (sj_probe_start / sj_probe_stop): CUDA events around every launch whose
   // role starts with `probe_role`, recorded on the launching stream

@@ -222,7 +222,7 @@ void launch_mode(Ctx& c, const GemmP& p) {
 
 }  // namespace
 
-void gemm(Ctx& c, const GemmP& p) {
+void gemm_simt(Ctx& c, const GemmP& p) {
   if (!c.ok()) return;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K % BK) != 0 || (p.N % 4) != 0 || (p.ldw % 4) != 0 ||
       (p.ldc % 4) != 0 || (p.R && (p.ldr % 4) != 0)) {

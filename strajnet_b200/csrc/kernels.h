@@ -40,8 +40,42 @@ struct GemmP {
   // A_CONV3: output H x Wd, input (H>>up) x (Wd>>up) x Cin, M = images*H*Wd, K = 9*Cin
   // A_MERGE: input H x Wd x Cin, M = B*(H/2)*(Wd/2), K = 4*Cin
   int H = 0, Wd = 0, Cin = 0, up = 0;
+  // optional tensor-core copy of W (SjLinear.w_tc / tc_colsum / tc_bias), used when dtype == SJ_BF16
+  const void* W_tc = nullptr;
+  const float* tc_colsum = nullptr;
+  const float* tc_bias = nullptr;
+  void set_weights(const SjLinear& w) {
+    W = w.w; bias = w.b; W_tc = w.w_tc; tc_colsum = w.tc_colsum; tc_bias = w.tc_bias;
+  }
 };
+// dispatcher: tcgen05 kernel when dtype == SJ_BF16 and the shape/weights allow it, else the SIMT kernel
 void gemm(Ctx& c, const GemmP& p);
+void gemm_simt(Ctx& c, const GemmP& p);
+
+// ---- tcgen05 dense GEMM (tc_gemm.cu) -------------------------------------------------------------
+struct TcGemmP {
+  const void* A = nullptr;  // bf16
+  int a_mode = 0;           // 0: rows [M,K] (lda); 1: rows ordered [outer][G][inner]; 2: PatchMerging gather of [B,H,W,C]
+  int lda = 0, a_inner = 0;
+  int mH = 0, mW = 0, mC = 0;
+  const void* Bw = nullptr;  // bf16 [G][N][K]
+  int M = 0, N = 0, K = 0, groups = 1;
+  const float* bias = nullptr;
+  int bias_gstride = 0;
+  int act = ACT_NONE;
+  const void* R = nullptr;
+  int ldr = 0;
+  void* C = nullptr;
+  int ldc = 0;
+  RowMap cm;
+  const float* ln_mean = nullptr;
+  const float* ln_rstd = nullptr;
+  const float* ln_s = nullptr;  // column sums of the folded weights, [G][N]
+  int ln_gstride = 0;
+};
+bool tc_gemm_supported(const TcGemmP& p);
+void tc_gemm(Ctx& c, const TcGemmP& p);
+int num_sms();
 
 // ---- LayerNorm family (norm.cu) ---------------------------------------------------------------
 // per-row mean / rstd (biased variance) of x[rows, C] (row stride ld)
@@ -51,6 +85,9 @@ void ln_stats_merge(Ctx& c, const void* x, int B, int H, int W, int C, float eps
 // y = LN(x) * g + b (+ res); gamma/beta of group ((row / g_div) % g_mod)
 void layernorm(Ctx& c, const void* x, void* y, int rows, int C, const float* g, const float* b, float eps,
                const void* res, int g_div, int g_mod);
+// y[r] = LN(x[gather(r)]) with the gather map applied within blocks of map_len rows
+void layernorm_gather(Ctx& c, const void* x, void* y, int rows, int C, const float* g, const float* b, float eps,
+                      const int* map, int map_len);
 
 // ---- attention cores (attention.cu) -----------------------------------------------------------
 // Window attention core, modules.py:109-131.  qkv [nWinTotal*64, 3C] (q|k|v, head-major inside),

@@ -67,11 +67,14 @@ __global__ void ln_stats_merge_kernel(const T* __restrict__ x, int B, int H, int
 
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, const float* __restrict__ g,
-                                 const float* __restrict__ b, float eps, const T* __restrict__ res, int g_div, int g_mod) {
+                                 const float* __restrict__ b, float eps, const T* __restrict__ res, int g_div, int g_mod,
+                                 const int* __restrict__ map, int map_len) {
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  const T* p = x + (long long)row * C;
+  long long src = row;
+  if (map) src = (long long)(row / map_len) * map_len + map[row % map_len];
+  const T* p = x + src * C;
   int grp = (row / g_div) % g_mod;
   const float* gg = g + (long long)grp * C;
   const float* bb = b + (long long)grp * C;
@@ -131,9 +134,20 @@ void layernorm(Ctx& c, const void* x, void* y, int rows, int C, const float* g, 
   if (g_mod <= 0) g_mod = 1;
   int grid = cdiv(rows, 8);
   if (c.dtype == SJ_BF16)
-    SJ_LAUNCH(c, "layernorm", layernorm_kernel<bf16>, grid, 256, 0, (const bf16*)x, (bf16*)y, rows, C, g, b, eps, (const bf16*)res, g_div, g_mod);
+    SJ_LAUNCH(c, "layernorm", layernorm_kernel<bf16>, grid, 256, 0, (const bf16*)x, (bf16*)y, rows, C, g, b, eps, (const bf16*)res, g_div, g_mod, (const int*)nullptr, 0);
   else
-    SJ_LAUNCH(c, "layernorm", layernorm_kernel<float>, grid, 256, 0, (const float*)x, (float*)y, rows, C, g, b, eps, (const float*)res, g_div, g_mod);
+    SJ_LAUNCH(c, "layernorm", layernorm_kernel<float>, grid, 256, 0, (const float*)x, (float*)y, rows, C, g, b, eps, (const float*)res, g_div, g_mod, (const int*)nullptr, 0);
+}
+
+void layernorm_gather(Ctx& c, const void* x, void* y, int rows, int C, const float* g, const float* b, float eps,
+                      const int* map, int map_len) {
+  if (!c.ok() || c.dry) return;
+  if (C % 4 || !map || map_len <= 0) { c.fail(SJ_EINVAL); return; }
+  int grid = cdiv(rows, 8);
+  if (c.dtype == SJ_BF16)
+    SJ_LAUNCH(c, "layernorm_gather", layernorm_kernel<bf16>, grid, 256, 0, (const bf16*)x, (bf16*)y, rows, C, g, b, eps, (const bf16*)nullptr, 1, 1, map, map_len);
+  else
+    SJ_LAUNCH(c, "layernorm_gather", layernorm_kernel<float>, grid, 256, 0, (const float*)x, (float*)y, rows, C, g, b, eps, (const float*)nullptr, 1, 1, map, map_len);
 }
 
 }  // namespace sj

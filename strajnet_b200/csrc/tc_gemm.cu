@@ -1,0 +1,366 @@
+// Dense bf16 GEMM on the 5th-gen tensor cores: C = [R +] act(LNfold(A . W^T) + bias).
+//
+//   * persistent: grid = #SMs, each CTA strides over (group, m-tile, n-tile) work items;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer,
+//     warps 2..5 = epilogue (TMEM lane quarter = warp % 4);
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B, 64-element K blocks) through a
+//     4-stage mbarrier ring; accumulators live in TMEM (fp32, 128 lanes x BN columns), double
+//     buffered so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * epilogue: tcgen05.ld -> LayerNorm fold / bias / GELU|ELU / residual -> bf16 -> global.
+//
+// LayerNorm fold: LN(x).W + b == rstd*(x.(g*W) - mean*colsum(g*W)) + (beta.W + b), so the raw
+// activations go through TMA untouched and the per-row affine is applied in the epilogue.
+#include <cstdio>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace sj {
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+struct KParams {
+  int M, N, K, BN, groups, m_tiles, n_tiles, k_blocks;
+  int a_mode, a_inner;  // a_mode 1: rows = [outer][G][inner]
+  int mWo, mHoTile;     // a_mode 2 (PatchMerging): merged width, merged rows per m-tile
+  int mC;
+  const float* bias;
+  int bias_gstride;
+  int act;
+  const bf16* R;
+  int ldr;
+  bf16* C;
+  int ldc;
+  RowMap cm;
+  const float* ln_mean;
+  const float* ln_rstd;
+  const float* ln_s;
+  int ln_gstride;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.BN * BK * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * b_stage_bytes);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_group = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_per_group * p.groups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int g = tile / tiles_per_group, rem = tile % tiles_per_group;
+        const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int m0 = mt * BM, n0 = nt * p.BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + b_stage_bytes);
+          void* da = smem_a + stage * A_STAGE_BYTES;
+          int k0 = kb * BK;
+          if (p.a_mode == 0) {
+            tma_load_2d(da, &mapA, &full_bar[stage], k0, m0);
+          } else if (p.a_mode == 1) {
+            tma_load_4d(da, &mapA, &full_bar[stage], k0, m0 % p.a_inner, g, m0 / p.a_inner);
+          } else {
+            // PatchMerging gather: k = q*C + c, q -> (dy, dx) = (q & 1, q >> 1); view {C, 2(dx), W/2, 2(dy), B*H/2}
+            // C need not be a multiple of 64: each quadrant is covered by ceil(C/64) blocks; the channels a box
+            // reads past C are zero-filled by TMA, which cancels the weight columns of the next quadrant.
+            const int cpb = (p.mC + BK - 1) / BK;
+            const int q = kb / cpb, c0 = (kb % cpb) * BK;
+            const int r0 = (m0 / p.mWo);  // first merged row (b*Ho + i) of this tile
+            tma_load_5d(da, &mapA, &full_bar[stage], c0, q >> 1, 0, q & 1, r0);
+            k0 = q * p.mC + c0;
+          }
+          tma_load_3d(smem_b + stage * b_stage_bytes, &mapB, &full_bar[stage], k0, n0, g);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, p.BN);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES), 128);
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes), 128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K=16 step inside the 128B swizzle row
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp % 4;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int g = tile / tiles_per_group, rem = tile % tiles_per_group;
+      const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      const int m = mt * BM + quarter * 32 + lane;
+      const int n0 = nt * p.BN;
+      const bool valid = m < p.M;
+      long long crow = 0;
+      float mean = 0.f, rstd = 1.f;
+      if (valid) {
+        crow = m;
+        if (p.cm.inner > 0) crow = (long long)(m / p.cm.inner) * p.cm.outer + (m % p.cm.inner);
+        crow += (long long)g * p.cm.gstride;
+        if (p.cm.map) crow = (crow / p.cm.map_len) * p.cm.map_len + p.cm.map[crow % p.cm.map_len];
+        if (p.ln_mean) {
+          // LN statistics are indexed like the A rows
+          long long arow = m;
+          if (p.a_mode == 1) arow = ((long long)(m / p.a_inner) * p.groups + g) * p.a_inner + (m % p.a_inner);
+          mean = p.ln_mean[arow];
+          rstd = p.ln_rstd[arow];
+        }
+      }
+      const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
+      const float* lns = p.ln_s ? p.ln_s + (long long)g * p.ln_gstride : nullptr;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.BN;
+      for (int c = 0; c < p.BN; c += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c, v);
+        if (valid) {
+          const int n = n0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = v[i];
+            if (lns) x = rstd * (x - mean * lns[n + i]);
+            if (bias) x += bias[n + i];
+            v[i] = apply_act(x, p.act);
+          }
+          if (p.R) {
+            const bf16* r = p.R + crow * p.ldr + n;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 rv = ld4<bf16>(r + i);
+              v[i] += rv.x; v[i + 1] += rv.y; v[i + 2] += rv.z; v[i + 3] += rv.w;
+            }
+          }
+          bf16* dst = p.C + crow * p.ldc + n;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) st4<bf16>(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int pick_bn(int N) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+// ---- tensor-map encoder (driver entry point fetched at run time; no link-time libcuda dependency) -----
+bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle_bytes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr)
+      return false;
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+bool tc_gemm_supported(const TcGemmP& a) {
+  if (!a.Bw || a.K < 64 || a.K % 32 || a.N % 16 || pick_bn(a.N) == 0) return false;
+  if (a.a_mode == 0 && (a.lda % 8)) return false;
+  if (a.a_mode == 1 && (a.a_inner % BM)) return false;
+  if (a.a_mode == 2) {
+    int Wo = a.mW / 2;
+    if (a.mC % 32 || Wo <= 0 || BM % Wo || (a.mH / 2) % (BM / Wo) || a.K != 4 * a.mC) return false;
+  }
+  if (a.ldc % 8 || (a.R && a.ldr % 8)) return false;
+  return true;
+}
+
+void tc_gemm(Ctx& c, const TcGemmP& a) {
+  if (!c.ok() || c.dry) return;
+  if (!tc_gemm_supported(a)) { c.fail(SJ_EUNSUPPORTED); return; }
+  KParams p{};
+  p.M = a.M; p.N = a.N; p.K = a.K; p.groups = a.groups < 1 ? 1 : a.groups;
+  p.BN = pick_bn(a.N);
+  p.m_tiles = cdiv(a.M, BM);
+  p.n_tiles = a.N / p.BN;
+  p.k_blocks = a.a_mode == 2 ? 4 * cdiv(a.mC, BK) : cdiv(a.K, BK);
+  p.a_mode = a.a_mode; p.a_inner = a.a_inner;
+  p.bias = a.bias; p.bias_gstride = a.bias_gstride; p.act = a.act;
+  p.R = (const bf16*)a.R; p.ldr = a.ldr; p.C = (bf16*)a.C; p.ldc = a.ldc; p.cm = a.cm;
+  p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_s = a.ln_s; p.ln_gstride = a.ln_gstride;
+
+  CUtensorMap mapA, mapB;
+  bool ok = true;
+  if (a.a_mode == 0) {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {BK, BM};
+    ok = encode_tmap(&mapA, a.A, 2, dims, str, box, 128);
+  } else if (a.a_mode == 1) {
+    // rows ordered [outer][G][inner]; M counts rows per group = outer*inner
+    uint64_t outer = (uint64_t)a.M / a.a_inner;
+    uint64_t dims[4] = {(uint64_t)a.K, (uint64_t)a.a_inner, (uint64_t)p.groups, outer};
+    uint64_t str[3] = {(uint64_t)a.lda * 2, (uint64_t)a.lda * 2 * a.a_inner, (uint64_t)a.lda * 2 * a.a_inner * p.groups};
+    uint32_t box[4] = {BK, BM, 1, 1};
+    ok = encode_tmap(&mapA, a.A, 4, dims, str, box, 128);
+  } else {
+    const int C = a.mC, H = a.mH, W = a.mW, Wo = W / 2;
+    const uint64_t rows = (uint64_t)a.M / Wo;  // B * H/2
+    p.mWo = Wo; p.mHoTile = BM / Wo; p.mC = C;
+    uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)Wo, 2, rows};
+    uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)W * C * 2, (uint64_t)W * C * 4};
+    uint32_t box[5] = {BK, 1, (uint32_t)Wo, 1, (uint32_t)(BM / Wo)};
+    ok = encode_tmap(&mapA, a.A, 5, dims, str, box, 128);
+    (void)H;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)p.groups};
+    uint64_t str[2] = {(uint64_t)a.K * 2, (uint64_t)a.K * 2 * a.N};
+    uint32_t box[3] = {BK, (uint32_t)p.BN, 1};
+    ok = ok && encode_tmap(&mapB, a.Bw, 3, dims, str, box, 128);
+  }
+  if (!ok) {
+    snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_gemm M=%d N=%d K=%d)", a.M, a.N, a.K);
+    c.fail(SJ_ECUDA);
+    return;
+  }
+  const size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + p.BN * BK * 2) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      c.fail(SJ_ECUDA);
+      return;
+    }
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.groups;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
+  const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
+  SJ_LAUNCH(c, "tc_gemm", tc_gemm_kernel, grid, NTHREADS, smem_launch, mapA, mapB, p);
+}
+
+// ---- dispatcher ------------------------------------------------------------------------------------
+void gemm(Ctx& c, const GemmP& g) {
+  if (!c.ok()) return;
+  if (c.dtype == SJ_BF16 && g.W_tc && g.amode != A_CONV3 && !g.am.map) {
+    const bool ln = g.ln_mean != nullptr;
+    // a folded tensor-core copy can only serve the LayerNorm'ed use of the layer, and vice versa
+    if (ln == (g.tc_colsum != nullptr)) {
+      TcGemmP t;
+      bool ok = true;
+      t.A = g.A; t.lda = g.lda;
+      if (g.amode == A_MERGE) {
+        t.a_mode = 2; t.mH = g.H; t.mW = g.Wd; t.mC = g.Cin;
+      } else if (g.am.inner > 0) {
+        // rows [outer][G][inner] visited per group: outer stride must be G*inner and group stride inner
+        ok = g.am.outer == g.groups * g.am.inner && g.am.gstride == g.am.inner;
+        t.a_mode = 1; t.a_inner = g.am.inner;
+      } else {
+        ok = g.am.gstride == 0;
+        t.a_mode = 0;
+      }
+      t.Bw = g.W_tc; t.M = g.M; t.N = g.N; t.K = g.K; t.groups = g.groups;
+      t.bias = ln ? g.tc_bias : g.bias; t.bias_gstride = g.bias_gstride; t.act = g.act;
+      t.R = g.R; t.ldr = g.ldr; t.C = g.C; t.ldc = g.ldc; t.cm = g.cm;
+      if (ln) {
+        t.ln_mean = g.ln_mean; t.ln_rstd = g.ln_rstd; t.ln_s = g.tc_colsum;
+        t.ln_gstride = g.groups > 1 ? g.N : 0;
+        if (g.groups > 1) t.bias_gstride = g.N;
+      }
+      if (ok && (g.groups == 1 || g.w_gstride == (long long)g.K * g.N) && tc_gemm_supported(t)) {
+        tc_gemm(c, t);
+        return;
+      }
+    }
+  }
+  gemm_simt(c, g);
+}
+
+}  // namespace sj

@@ -168,6 +168,37 @@ def window_token_map(H: int, Wd: int, window_size: int, shift_size: int, device=
 
 
 # ------------------------------------------------------------------------------------------------
+class Dense(Layer):
+    """keras.layers.Dense as the reference uses it (modules.py:36-37,76,79,270; trajNet.py:35-36,74-76,...)."""
+    _ACT = {None: 0, "linear": 0, "gelu": 1, "elu": 2}
+
+    def __init__(self, units, in_features, activation=None, use_bias=True, **kw):
+        super().__init__(**kw)
+        if activation not in self._ACT:
+            raise ValueError(f"Dense: unsupported activation {activation!r}")
+        self.units, self.in_features, self.activation, self.use_bias = units, in_features, activation, use_bias
+
+    def weight_shapes(self):
+        s = {"kernel": (self.in_features, self.units)}
+        if self.use_bias:
+            s["bias"] = (self.units,)
+        return s
+
+    def _pack(self):
+        p = self._packer()
+        return p.linear(p.get("kernel"), p.get("bias") if self.use_bias else None), p
+
+    def call(self, x):
+        x = self._act(x)
+        if x.shape[-1] != self.in_features:
+            raise ValueError(f"Dense: last dim {x.shape[-1]} != {self.in_features}")
+        M = x.numel() // self.in_features
+        y = self._new(*x.shape[:-1], self.units)
+        L.check(L.lib().sj_dense_fwd(x.data_ptr(), y.data_ptr(), C.byref(self.packed()), M, self.units, self.in_features,
+                                     self._ACT[self.activation], self.sj_dtype, _stream()), "Dense")
+        return y
+
+
 class Mlp(Layer):
     """modules.py:31-46."""
 

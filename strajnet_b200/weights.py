@@ -271,14 +271,24 @@ class Packer:
             raise KeyError(f"missing weight '{name}'")
         return self.w[name].to(torch.float32)
 
-    def linear(self, kernel: Tensor, bias: Optional[Tensor], tc_kernel: Optional[Tensor] = None) -> L.SjLinear:
-        """kernel: [K,N] (or stacked [G,K,N]); tc copy is [N,K] (or [G,N,K]) bf16 unless given explicitly."""
+    def linear(self, kernel: Tensor, bias: Optional[Tensor], tc_kernel: Optional[Tensor] = None,
+               ln: Optional[tuple] = None) -> L.SjLinear:
+        """kernel: [K,N] (or stacked [G,K,N]); tc copy is [N,K] (or [G,N,K]) bf16 unless given explicitly.
+        ln = (gamma [.., K], beta [.., K]): fold the preceding LayerNorm into the tensor-core copy."""
         s = L.SjLinear()
         s.w = self.ptr(kernel)
         s.b = self.ptr(bias)
         if self.tc:
-            t = tc_kernel if tc_kernel is not None else kernel.transpose(-1, -2)
-            s.w_tc = self.ptr(t, torch.bfloat16)
+            if ln is not None:
+                g, b = ln[0].to(torch.float32), ln[1].to(torch.float32)
+                folded = (kernel * g.unsqueeze(-1)).transpose(-1, -2).to(torch.bfloat16)  # [.., N, K]
+                s.w_tc = self.ptr(folded, torch.bfloat16)
+                s.tc_colsum = self.ptr(folded.to(torch.float32).sum(-1))
+                tb = (b.unsqueeze(-1).to(torch.float64) * kernel.to(torch.float64)).sum(-2).to(torch.float32)
+                s.tc_bias = self.ptr(tb + bias if bias is not None else tb)
+            else:
+                t = tc_kernel if tc_kernel is not None else kernel.transpose(-1, -2)
+                s.w_tc = self.ptr(t, torch.bfloat16)
         return s
 
     def norm(self, prefix: str) -> L.SjNorm:
@@ -295,14 +305,16 @@ class Packer:
         s.rpb_table = self.ptr(self.get(p + "attn.relative_position_bias_table"))
         s.proj = self.linear(self.get(p + "attn.proj.kernel"), self.get(p + "attn.proj.bias"))
         s.norm2 = self.norm(p + "norm2.")
-        s.fc1 = self.linear(self.get(p + "mlp.fc1.kernel"), self.get(p + "mlp.fc1.bias"))
+        s.fc1 = self.linear(self.get(p + "mlp.fc1.kernel"), self.get(p + "mlp.fc1.bias"),
+                            ln=(self.get(p + "norm2.gamma"), self.get(p + "norm2.beta")))
         s.fc2 = self.linear(self.get(p + "mlp.fc2.kernel"), self.get(p + "mlp.fc2.bias"))
         return s
 
     def patch_merge(self, p: str) -> L.SjPatchMergeW:
         s = L.SjPatchMergeW()
         s.norm = self.norm(p + "norm.")
-        s.reduction = self.linear(self.get(p + "reduction.kernel"), None)
+        s.reduction = self.linear(self.get(p + "reduction.kernel"), None,
+                                  ln=(self.get(p + "norm.gamma"), self.get(p + "norm.beta")))
         return s
 
     def patch_embed(self, p: str) -> L.SjPatchEmbedW:
@@ -372,7 +384,8 @@ class Packer:
                                          tfa_in_kernel(self.get(a + "mha.value_kernel"))], 1), None)
         s.ia_proj = self.linear(tfa_out_kernel(self.get(a + "mha.projection_kernel")), self.get(a + "mha.projection_bias"))
         s.ia_norm1 = self.norm(a + "norm1.")
-        s.ia_ffn1 = self.linear(self.get(a + "FFN1.kernel"), self.get(a + "FFN1.bias"))
+        s.ia_ffn1 = self.linear(self.get(a + "FFN1.kernel"), self.get(a + "FFN1.bias"),
+                                ln=(self.get(a + "norm1.gamma"), self.get(a + "norm1.beta")))
         s.ia_ffn2 = self.linear(self.get(a + "FFN2.kernel"), self.get(a + "FFN2.bias"))
         s.ia_norm2 = self.norm(a + "norm2.")
         s.obs_norm = self.norm(p + "traj_net.obs_norm.")
@@ -389,7 +402,8 @@ class Packer:
                                 stack(lambda q: self.get(q + "mha.projection_bias")))
         s.ca_norm1.g = self.ptr(stack(lambda q: self.get(q + "norm1.gamma")))
         s.ca_norm1.b = self.ptr(stack(lambda q: self.get(q + "norm1.beta")))
-        s.ca_ffn1 = self.linear(stack(lambda q: self.get(q + "FFN1.kernel")), stack(lambda q: self.get(q + "FFN1.bias")))
+        s.ca_ffn1 = self.linear(stack(lambda q: self.get(q + "FFN1.kernel")), stack(lambda q: self.get(q + "FFN1.bias")),
+                                ln=(stack(lambda q: self.get(q + "norm1.gamma")), stack(lambda q: self.get(q + "norm1.beta"))))
         s.ca_ffn2 = self.linear(stack(lambda q: self.get(q + "FFN2.kernel")), stack(lambda q: self.get(q + "FFN2.bias")))
         s.ca_norm2.g = self.ptr(stack(lambda q: self.get(q + "norm2.gamma")))
         s.ca_norm2.b = self.ptr(stack(lambda q: self.get(q + "norm2.beta")))
