@@ -347,6 +347,10 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
 
 // ---- Pyramid3DDecoder.call (modules.py:739-772) --------------------------------------------------
 void upconv(Ctx& c, const void* x, void* y, const SjLinear& w, int NB, int Hin, int Cin, int Cout) {
+  if (c.dtype == SJ_BF16 && w.w_tc && w.b && tc_upconv_supported(Hin, Hin, Cin, Cout)) {
+    tc_upconv(c, x, y, w.w_tc, w.b, NB, Hin, Hin, Cin, Cout);
+    return;
+  }
   GemmP g;
   g.amode = A_CONV3; g.A = x; g.H = 2 * Hin; g.Wd = 2 * Hin; g.Cin = Cin; g.up = 1;
   g.set_weights(w); g.ldw = Cout; g.C = y; g.ldc = Cout;

@@ -77,6 +77,13 @@ bool tc_gemm_supported(const TcGemmP& p);
 void tc_gemm(Ctx& c, const TcGemmP& p);
 int num_sms();
 
+// ---- tcgen05 decoder up-convolution (tc_conv.cu) ---------------------------------------------------
+bool tc_upconv_supported(int H, int W, int Cin, int Cout);
+// x bf16 [NB,H,W,Cin] -> y bf16 [NB,2H,2W,Cout] = ELU(conv3x3_SAME(nearest_up2(x)) + bias); w_tc = sub-pixel folded
+// kernels [4 phases][Cout][4*Cin] bf16
+void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bias, int NB, int H, int W, int Cin,
+               int Cout);
+
 // ---- LayerNorm family (norm.cu) ---------------------------------------------------------------
 // per-row mean / rstd (biased variance) of x[rows, C] (row stride ld)
 void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* mean, float* rstd);
