@@ -181,6 +181,12 @@ int sj_window_reverse_fwd(const void* windows, void* x, int B, int H, int W, int
  * act 0 none, 1 tanh-GELU (modules.py:18), 2 ELU */
 int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K, int act, int dtype, sj_stream_t stream);
 
+/* Hardware-semantics probe (not part of the model path): y[m] = x[m + shift] . w_tc^T computed by pointing the
+ * UMMA shared-memory descriptor `shift` rows (128 B each) into a 128B-swizzled TMA tile, with or without the
+ * descriptor's base_offset field.  Documents whether shifted views of one staged tile are usable. */
+int sj_debug_gemm_shift(const void* x, void* y, const void* w_tc, int M, int N, int K, int shift, int use_base_offset,
+                        sj_stream_t stream);
+
 /* Mlp.call, modules.py:40-46: y = fc2(Gelu(fc1(x))), x [M,C] */
 size_t sj_mlp_workspace_bytes(int M, int C, int hidden, int dtype);
 int sj_mlp_fwd(const void* x, void* y, const SjLinear* fc1, const SjLinear* fc2, int M, int C, int hidden,

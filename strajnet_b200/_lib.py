@@ -93,6 +93,7 @@ SIGNATURES = {
     "sj_window_partition_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sj_window_reverse_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sj_dense_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
+    "sj_debug_gemm_shift": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sj_mlp_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sj_mlp_fwd": (_i, [_p, _p, C.POINTER(SjLinear), C.POINTER(SjLinear), _i, _i, _i, _i, _p, _sz, _p]),
     "sj_window_attention_workspace_bytes": (_sz, [_i, _i, _i]),

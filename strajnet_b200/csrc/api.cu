@@ -591,6 +591,18 @@ int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K,
   return run(nullptr, 0, dtype, stream, [&](Ctx& c) { linear(c, x, K, *w, y, N, M, N, K, act); });
 }
 
+// ---- hardware probe ----
+int sj_debug_gemm_shift(const void* x, void* y, const void* w_tc, int M, int N, int K, int shift, int use_base_offset,
+                        sj_stream_t stream) {
+  SJ_REQUIRE(x && y && w_tc && M > 0 && shift >= 0 && shift < 128);
+  return run(nullptr, 0, SJ_BF16, stream, [&](Ctx& c) {
+    TcGemmP t;
+    t.A = x; t.lda = K; t.Bw = w_tc; t.M = M; t.N = N; t.K = K; t.C = y; t.ldc = N;
+    t.dbg_shift = shift; t.dbg_bo = use_base_offset;
+    tc_gemm(c, t);
+  });
+}
+
 // ---- WindowAttention ----
 static void wattn_body(Ctx& c, const void* xw, void* y, const SjSwinBlockW* w, int B_, int C, int heads, const float* mask,
                        int nW) {

@@ -72,6 +72,7 @@ struct TcGemmP {
   const float* ln_rstd = nullptr;
   const float* ln_s = nullptr;  // column sums of the folded weights, [G][N]
   int ln_gstride = 0;
+  int dbg_shift = 0, dbg_bo = 0;  // hardware-semantics probe (sj_debug_gemm_shift)
 };
 bool tc_gemm_supported(const TcGemmP& p);
 void tc_gemm(Ctx& c, const TcGemmP& p);

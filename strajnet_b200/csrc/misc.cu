@@ -343,48 +343,91 @@ __global__ void traj_final_kernel(const T* __restrict__ E, const T* __restrict__
 }
 
 // ---------------------------------------------------------------- decoder head (K10)
-// thread per output pixel of one waypoint image; both 48->2 convs; writes 4 floats
+// Two 3x3 48->2 convs (output_layer on x, output_layer_f on fx; modules.py:767-770) + the final
+// [B,8,256,256,4] -> [B,256,256,32] transpose (:838).  HBM/FMA-bound CUDA-core kernel: one block per
+// (sample, 16x32 pixel tile) loops over the 8 waypoints x 2 heads, staging each 18x34 halo tile in
+// shared memory (112-byte pixel stride: conflict-free 16-byte reads), 4 pixels per thread, and writes
+// every pixel's 32 output channels as one contiguous 128-byte line.
+constexpr int OC_TY = 16, OC_TX = 32, OC_PSTRIDE = 56;  // pixel stride in bf16 elements (112 B)
+
 template <typename T>
-__global__ void out_conv_kernel(const T* __restrict__ xo, const T* __restrict__ xf, const float* __restrict__ w,
-                                const float* __restrict__ bias, int NB, int out_layout, float* __restrict__ out) {
-  __shared__ __align__(16) float ws[2 * 432 * 2];
-  for (int i = threadIdx.x; i < 2 * 432 * 2; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)NB * 65536) return;
-  int x = i % 256, y = (i / 256) % 256;
-  long long img = i / 65536;
-  float r[4] = {bias[0], bias[1], bias[2], bias[3]};
+__global__ void __launch_bounds__(128) out_conv_kernel(const T* __restrict__ xo, const T* __restrict__ xf,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int out_layout, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t oc_smem[];
+  T* tile = reinterpret_cast<T*>(oc_smem);                                                       // [18][34][56]
+  float2* ws = reinterpret_cast<float2*>(oc_smem + (OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * sizeof(T));  // [2][432]
+  const int tid = threadIdx.x, ty = tid / 8, tx = tid % 8;
+  const int b = blockIdx.z, y0 = blockIdx.y * OC_TY, x0 = blockIdx.x * OC_TX;
+  for (int i = tid; i < 864; i += 128) ws[i] = make_float2(w[2 * i], w[2 * i + 1]);
+  float acc[4][32];
 #pragma unroll
-  for (int head = 0; head < 2; ++head) {
-    const T* src = head == 0 ? xo : xf;
-    const float* wh = ws + head * 864;
-    float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[j][k] = 0.f;
+
+#pragma unroll
+  for (int th = 0; th < 16; ++th) {  // (waypoint t, head): fully unrolled so acc[][] stays in registers
+    const int t = th >> 1, head = th & 1;
+    const T* src = (head == 0 ? xo : xf) + ((long long)(b * 8 + t) * 65536) * 48;
+    __syncthreads();
+    constexpr int VE = 16 / sizeof(T);  // elements per 16-byte vector
+    constexpr int VPP = 48 / VE;        // vectors per pixel
+    for (int i = tid; i < (OC_TY + 2) * (OC_TX + 2) * VPP; i += 128) {
+      const int ch = i % VPP, pix = i / VPP, px = pix % (OC_TX + 2), py = pix / (OC_TX + 2);
+      const int yy = y0 + py - 1, xx = x0 + px - 1;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (yy >= 0 && yy < 256 && xx >= 0 && xx < 256)
+        v = *reinterpret_cast<const uint4*>(src + ((long long)yy * 256 + xx) * 48 + ch * VE);
+      *reinterpret_cast<uint4*>(tile + pix * OC_PSTRIDE + ch * VE) = v;
+    }
+    __syncthreads();
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    const float2* wh = ws + head * 432;
+#pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
-      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= 256 || xx < 0 || xx >= 256) continue;
-      const T* px = src + ((img * 256 + yy) * 256 + xx) * 48;
-      const float* wt = wh + tap * 96;
+      const T* row = tile + ((ty + tap / 3) * (OC_TX + 2) + tx + tap % 3) * OC_PSTRIDE;
 #pragma unroll
-      for (int c = 0; c < 48; c += 4) {
-        float4 v = ld4<T>(px + c);
-        a0 = fmaf(v.x, wt[2 * c], a0);     a1 = fmaf(v.x, wt[2 * c + 1], a1);
-        a0 = fmaf(v.y, wt[2 * c + 2], a0); a1 = fmaf(v.y, wt[2 * c + 3], a1);
-        a0 = fmaf(v.z, wt[2 * c + 4], a0); a1 = fmaf(v.z, wt[2 * c + 5], a1);
-        a0 = fmaf(v.w, wt[2 * c + 6], a0); a1 = fmaf(v.w, wt[2 * c + 7], a1);
+      for (int ch = 0; ch < 48; ch += 8) {
+        float xv[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 lo = ld4<T>(row + j * 8 * OC_PSTRIDE + ch), hi = ld4<T>(row + j * 8 * OC_PSTRIDE + ch + 4);
+          xv[j][0] = lo.x; xv[j][1] = lo.y; xv[j][2] = lo.z; xv[j][3] = lo.w;
+          xv[j][4] = hi.x; xv[j][5] = hi.y; xv[j][6] = hi.z; xv[j][7] = hi.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 wv = wh[tap * 48 + ch + e];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a0[j] = fmaf(xv[j][e], wv.x, a0[j]);
+            a1[j] = fmaf(xv[j][e], wv.y, a1[j]);
+          }
+        }
       }
     }
-    r[head * 2] += a0;
-    r[head * 2 + 1] += a1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j][t * 4 + head * 2] = a0[j] + bias[head * 2];
+      acc[j][t * 4 + head * 2 + 1] = a1[j] + bias[head * 2 + 1];
+    }
   }
-  long long o;
-  if (out_layout == 0) o = i * 4;                       // [B,8,256,256,4]
-  else {
-    long long b = img / 8;
-    int t = img % 8;
-    o = ((b * 256 + y) * 256 + x) * 32 + t * 4;         // [B,256,256,32], channel t*4+c (modules.py:838)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = y0 + ty, x = x0 + tx + 8 * j;
+    if (out_layout == 1) {
+      float* o = out + (((long long)b * 256 + y) * 256 + x) * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4)
+        *reinterpret_cast<float4*>(o + k) = make_float4(acc[j][k], acc[j][k + 1], acc[j][k + 2], acc[j][k + 3]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        *reinterpret_cast<float4*>(out + ((((long long)b * 8 + t) * 256 + y) * 256 + x) * 4) =
+            make_float4(acc[j][t * 4], acc[j][t * 4 + 1], acc[j][t * 4 + 2], acc[j][t * 4 + 3]);
+    }
   }
-  *reinterpret_cast<float4*>(out + o) = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 }  // namespace
@@ -473,10 +516,15 @@ void traj_final(Ctx& c, const void* E, const void* F2, const SjTrajW* w, int n_a
 void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, const float* b, int B, int out_layout,
               float* out) {
   if (!c.ok() || c.dry) return;
-  int NB = B * 8;
-  long long n = (long long)NB * 65536;
-  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "out_conv", out_conv_kernel<bf16>, cdiv(n, 128), 128, 0, (const bf16*)x_occ, (const bf16*)x_flow, w, b, NB, out_layout, out);
-  else SJ_LAUNCH(c, "out_conv", out_conv_kernel<float>, cdiv(n, 128), 128, 0, (const float*)x_occ, (const float*)x_flow, w, b, NB, out_layout, out);
+  dim3 grid(256 / OC_TX, 256 / OC_TY, B);
+  const size_t smem = (size_t)(OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * c.esize() + 864 * sizeof(float2);
+  if (c.dtype == SJ_BF16) {
+    if (cudaFuncSetAttribute(out_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+    SJ_LAUNCH(c, "out_conv", out_conv_kernel<bf16>, grid, 128, smem, (const bf16*)x_occ, (const bf16*)x_flow, w, b, out_layout, out);
+  } else {
+    if (cudaFuncSetAttribute(out_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+    SJ_LAUNCH(c, "out_conv", out_conv_kernel<float>, grid, 128, smem, (const float*)x_occ, (const float*)x_flow, w, b, out_layout, out);
+  }
 }
 
 }  // namespace sj

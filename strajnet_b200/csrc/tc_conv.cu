@@ -166,13 +166,22 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int px = 0; px < 2; ++px) {
         bf16* dst = p.out + (((long long)n * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px) * p.Cout;
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (as * 2 + px) * p.acs;
-        for (int c = 0; c < p.Cout; c += 16) {
+        int c = 0;
+        for (; c + 32 <= p.Cout; c += 32) {
+          float v[32];
+          tmem_ld32(t_addr + c, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i] + p.bias[c + i], ACT_ELU);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) st8_bf16(dst + c + i, v + i);
+        }
+        if (c < p.Cout) {
           float v[16];
           tmem_ld16(t_addr + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = elu1(v[i] + p.bias[c + i]);
+          for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i] + p.bias[c + i], ACT_ELU);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) st4<bf16>(dst + c + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 16; i += 8) st8_bf16(dst + c + i, v + i);
         }
       }
       tc_fence_before();

@@ -21,7 +21,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 192;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int A_STAGE_BYTES_MAX = 256 * BK * 2;
 
 struct KParams {
   int M, N, K, BN, groups, m_tiles, n_tiles, k_blocks;
@@ -40,6 +40,9 @@ struct KParams {
   const float* ln_rstd;
   const float* ln_s;
   int ln_gstride;
+  int a_rows;     // rows per A stage (128; 256 for the shifted-view probe)
+  int dbg_shift;  // probe: the MMA reads A rows [shift, shift+128) of the stage
+  int dbg_bo;     // probe: set the descriptor base_offset field from the start address
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -47,6 +50,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = p.BN * BK * 2;
+  const int A_STAGE_BYTES = p.a_rows * BK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * b_stage_bytes);
@@ -123,7 +127,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES), 128);
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES) + p.dbg_shift * 128;
+          uint64_t da = make_smem_desc(a_addr, 128);
+          if (p.dbg_bo) da |= (uint64_t)((a_addr >> 7) & 7) << 49;  // matrix base offset, bits [49,52)
           const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes), 128);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K=16 step inside the 128B swizzle row
@@ -165,30 +171,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.BN;
-      for (int c = 0; c < p.BN; c += 16) {
+      auto finish = [&](float* v, int n, int cnt) {  // LN fold / bias / activation / residual / store, cnt columns
+        if (!valid) return;
+        for (int i = 0; i < cnt; ++i) {
+          float x = v[i];
+          if (lns) x = rstd * (x - mean * lns[n + i]);
+          if (bias) x += bias[n + i];
+          v[i] = act_fast(x, p.act);
+        }
+        for (int i = 0; i < cnt; i += 8) {
+          if (p.R) {
+            float r[8];
+            ld8_bf16(p.R + crow * p.ldr + n + i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i + j] += r[j];
+          }
+          st8_bf16(p.C + crow * p.ldc + n + i, v + i);
+        }
+      };
+      int c = 0;
+      for (; c + 32 <= p.BN; c += 32) {
+        float v[32];
+        tmem_ld32(t_addr + c, v);
+#pragma unroll
+        for (int h = 0; h < 1; ++h) finish(v, n0 + c, 32);
+      }
+      if (c < p.BN) {
         float v[16];
         tmem_ld16(t_addr + c, v);
-        if (valid) {
-          const int n = n0 + c;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = v[i];
-            if (lns) x = rstd * (x - mean * lns[n + i]);
-            if (bias) x += bias[n + i];
-            v[i] = apply_act(x, p.act);
-          }
-          if (p.R) {
-            const bf16* r = p.R + crow * p.ldr + n;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 rv = ld4<bf16>(r + i);
-              v[i] += rv.x; v[i + 1] += rv.y; v[i + 2] += rv.z; v[i + 3] += rv.w;
-            }
-          }
-          bf16* dst = p.C + crow * p.ldc + n;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) st4<bf16>(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        }
+        finish(v, n0 + c, 16);
       }
       tc_fence_before();
       __syncwarp();
@@ -274,13 +285,14 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   p.bias = a.bias; p.bias_gstride = a.bias_gstride; p.act = a.act;
   p.R = (const bf16*)a.R; p.ldr = a.ldr; p.C = (bf16*)a.C; p.ldc = a.ldc; p.cm = a.cm;
   p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_s = a.ln_s; p.ln_gstride = a.ln_gstride;
+  p.a_rows = a.dbg_shift > 0 ? 256 : BM; p.dbg_shift = a.dbg_shift; p.dbg_bo = a.dbg_bo;
 
   CUtensorMap mapA, mapB;
   bool ok = true;
   if (a.a_mode == 0) {
-    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M + (a.dbg_shift > 0 ? 256 : 0)};  // the probe reads past M
     uint64_t str[1] = {(uint64_t)a.lda * 2};
-    uint32_t box[2] = {BK, BM};
+    uint32_t box[2] = {BK, (uint32_t)p.a_rows};
     ok = encode_tmap(&mapA, a.A, 2, dims, str, box, 128);
   } else if (a.a_mode == 1) {
     // rows ordered [outer][G][inner]; M counts rows per group = outer*inner
@@ -310,7 +322,7 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + p.BN * BK * 2) + 256;
+  const size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
