@@ -2,15 +2,22 @@
 // (modules.py:746-749), executed as four 2x2 sub-pixel convolutions on the LOW-RES input with
 // pre-summed taps (weights.fold_upconv_subpixel): 2.25x fewer FLOPs, 4x fewer input bytes.
 //
-// Implicit GEMM, no im2col buffer: one work item = (image, 8x16 low-res pixel tile, output row phase py).
-// It produces both column phases px in two TMEM accumulators [128 pixels x Cout].  The K loop walks
-// the 2 row taps x 3 column taps x Cin chunks; for every tap the A tile is ONE 4-D TMA box
-// {channels, 16, 8, 1} of the NHWC input at a shifted origin -- out-of-image rows/columns are
-// zero-filled by TMA, which is exactly the SAME padding.  A column tap feeds one (dx = +-1) or two
-// (dx = 0) column phases, so the matching folded weight tiles [Cout x chunk] ride in the same stage.
-//
-// Same skeleton as tc_gemm.cu: persistent CTAs, warp 0 = TMA, warp 1 = tcgen05.mma, warps 2..5 =
-// epilogue, mbarrier ring, accumulators double-buffered in TMEM when 4*Cout fits 512 columns.
+// Implicit GEMM without an im2col buffer and without re-reading the input per tap:
+//   * work item = (image, 16x8 low-res pixel tile, output row phase py); both column phases px are
+//     produced in two TMEM accumulators [128 pixels x Cout];
+//   * per Cin chunk ONE 4-D TMA box {channels, 10, 17, 1} stages the tile plus its halo (rows y0-1+py..,
+//     columns x0-1..x0+8) in shared memory; out-of-image rows/columns are zero-filled by TMA, which
+//     is exactly the SAME padding of the reference conv;
+//   * each of the 2x3 taps is a *shifted view* of that one patch: the UMMA descriptor starts
+//     (a*10 + dx+1) pixel rows into the patch and uses stride_byte_offset = 10 pixel rows, so MMA row
+//     r = 8*ty+tx reads patch pixel (ty+a, tx+dx+1).  The 128B/64B swizzle is a function of the
+//     absolute shared-memory address (verified on B200 by tools/probe_shift.py), so views that are
+//     not aligned to the swizzle atom read exactly what TMA wrote;
+//   * folded weights [4 phases][Cout][4*Cin] either stream through an mbarrier ring (large layers) or,
+//     when the 8 tiles of one row phase fit (the 96->48 layer), stay resident in shared memory
+//     for the whole persistent CTA;
+//   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue (bias + ELU + bf16,
+//     16-byte stores); accumulators double-buffered in TMEM when 4*Cout fits 512 columns.
 #include <cstdio>
 
 #include "kernels.h"
@@ -21,43 +28,62 @@ namespace {
 
 using namespace tc;
 
-constexpr int TH = 8, TW = 16, BM = 128, NTHREADS = 192;
+constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 2, BM = 128, NTHREADS = 192;
+constexpr int MAX_STAGES = 8;
 
 struct ConvP {
   int NB, H, W, Cin, Cout;  // low-res input geometry
-  int tiles_x, tiles_y, num_items;
+  int tiles_x, tiles_y, num_tiles;
   int acs;                  // TMEM column stride between accumulators
   int nacc;                 // accumulator stages (1 or 2)
-  int stages;
+  int na, nbs;              // A-patch slots, B stages (streaming mode)
+  int a_slot;               // bytes per A slot (all chunks of a group, each 1024-aligned)
+  int a_sub;                // bytes per chunk sub-patch (padded to 1024)
   const float* bias;
   bf16* out;                // [NB, 2H, 2W, Cout]
 };
 
-// KC: channels per swizzled smem row (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NCH: chunks per pipeline stage
-template <int KC, int NCH>
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t addr, uint32_t row_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
+  return d;
+}
+
+// KC: channels per swizzled smem row (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NCH: chunks per A slot;
+// RESB: weights of this CTA's row phase resident in shared memory
+template <int KC, int NCH, bool RESB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int ROWB = KC * 2;                 // bytes per smem row
-  constexpr int A_SUB = BM * ROWB;             // one A chunk
-  const int b_sub = p.Cout * ROWB;             // one B chunk of one phase
-  const int a_stage = NCH * A_SUB;
-  const int stage_bytes = a_stage + 2 * NCH * b_sub;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + p.stages;
-  uint64_t* tfull_bar = bars + 2 * p.stages;
-  uint64_t* tempty_bar = bars + 2 * p.stages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  constexpr int ROWB = KC * 2;
+  const int b_sub = p.Cout * ROWB;            // one weight tile: Cout rows x one chunk
+  const int b_stage = 2 * NCH * b_sub;        // streaming: up to two phases per tap
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.na * p.a_slot;
+  const int b_bytes = RESB ? 8 * NCH * b_sub : p.nbs * b_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + ((b_bytes + 1023) & ~1023));
+  uint64_t* afull = bars;                      // [na]
+  uint64_t* aempty = bars + MAX_STAGES;        // [na]
+  uint64_t* bfull = bars + 2 * MAX_STAGES;     // [nbs] (bfull[0] doubles as "weights resident")
+  uint64_t* bempty = bars + 3 * MAX_STAGES;    // [nbs]
+  uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -70,42 +96,53 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int groups_per_tap = p.Cin / (KC * NCH);
+
+  const int groups = p.Cin / (KC * NCH);       // A slots consumed per item
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // each CTA serves one row phase; tiles are strided over the CTAs of that phase
+  const int py = blockIdx.x & 1;
+  const int cta_in_phase = blockIdx.x >> 1, ctas_per_phase = gridDim.x >> 1;
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int py = item & 1, t = item >> 1;
+      if (RESB) {  // the 8 (px, a, b) tiles of this row phase, loaded once
+        mbar_expect_tx(&bfull[0], 8 * NCH * b_sub);
+        for (int px = 0; px < 2; ++px)
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+              for (int ch = 0; ch < NCH; ++ch)
+                tma_load_2d(smem_b + ((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub, &mapB, &bfull[0],
+                            (a * 2 + b) * p.Cin + ch * KC, (py * 2 + px) * p.Cout);
+      }
+      int as_ = 0, bs_ = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
         const int n = t / tiles_per_img, tr = t % tiles_per_img;
         const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;
-        for (int a = 0; a < 2; ++a) {
-          const int dy = a - 1 + py;
-          for (int dxi = 0; dxi < 3; ++dxi) {
-            const int dx = dxi - 1;
-            for (int cg = 0; cg < groups_per_tap; ++cg) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * stage_bytes;
-              uint8_t* sb = sa + a_stage;
-              const int nb = dx == 0 ? 2 : 1;
-              mbar_expect_tx(&full_bar[stage], a_stage + nb * NCH * b_sub);
+        for (int cg = 0; cg < groups; ++cg) {
+          mbar_wait(&aempty[as_], aph ^ 1);
+          mbar_expect_tx(&afull[as_], NCH * PH * PW * ROWB);
 #pragma unroll
-              for (int ch = 0; ch < NCH; ++ch)
-                tma_load_4d(sa + ch * A_SUB, &mapA, &full_bar[stage], (cg * NCH + ch) * KC, x0 + dx, y0 + dy, n);
-              // slot 0: first phase fed by this column tap, slot 1: second (dx == 0 only)
-              for (int s = 0; s < nb; ++s) {
-                const int px = dx < 0 ? 0 : (dx > 0 ? 1 : s);
-                const int b = dx - px + 1;  // column tap index inside phase px: low-res offset = b - 1 + px
-                const int krow = ((a * 2 + b) * p.Cin);
+          for (int ch = 0; ch < NCH; ++ch)
+            tma_load_4d(smem_a + as_ * p.a_slot + ch * p.a_sub, &mapA, &afull[as_], (cg * NCH + ch) * KC, x0 - 1,
+                        y0 - 1 + py, n);
+          if (++as_ == p.na) { as_ = 0; aph ^= 1; }
+          if (!RESB) {
+            for (int a = 0; a < 2; ++a)
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                const int dx = dxi - 1, nb = dx == 0 ? 2 : 1;
+                mbar_wait(&bempty[bs_], bph ^ 1);
+                mbar_expect_tx(&bfull[bs_], nb * NCH * b_sub);
+                for (int s = 0; s < nb; ++s) {
+                  const int px = dx < 0 ? 0 : (dx > 0 ? 1 : s);
+                  const int b = dx - px + 1;  // column tap inside phase px: low-res offset = b - 1 + px
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch)
-                  tma_load_2d(sb + (s * NCH + ch) * b_sub, &mapB, &full_bar[stage], krow + (cg * NCH + ch) * KC,
-                              (py * 2 + px) * p.Cout);
+                  for (int ch = 0; ch < NCH; ++ch)
+                    tma_load_2d(smem_b + bs_ * b_stage + (s * NCH + ch) * b_sub, &mapB, &bfull[bs_],
+                                (a * 2 + b) * p.Cin + (cg * NCH + ch) * KC, (py * 2 + px) * p.Cout);
+                }
+                if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
               }
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            }
           }
         }
       }
@@ -113,28 +150,38 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, p.Cout);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+      int as_ = 0, bs_ = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, tph = 0;
+      if (RESB) {
+        mbar_wait(&bfull[0], 0);
+        tc_fence_after();
+      }
+      for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
+        mbar_wait(&tempty_bar[acc], tph ^ 1);
         tc_fence_after();
         uint32_t started[2] = {0, 0};
-        for (int a = 0; a < 2; ++a) {
-          for (int dxi = 0; dxi < 3; ++dxi) {
-            const int dx = dxi - 1;
-            for (int cg = 0; cg < groups_per_tap; ++cg) {
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-              const uint32_t sb = sa + a_stage;
-              const int nb = dx == 0 ? 2 : 1;
+        for (int cg = 0; cg < groups; ++cg) {
+          mbar_wait(&afull[as_], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + as_ * p.a_slot);
+          for (int a = 0; a < 2; ++a)
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              const int dx = dxi - 1, nb = dx == 0 ? 2 : 1;
+              if (!RESB) {
+                mbar_wait(&bfull[bs_], bph);
+                tc_fence_after();
+              }
               for (int s = 0; s < nb; ++s) {
                 const int px = dx < 0 ? 0 : (dx > 0 ? 1 : s);
-                const uint32_t d_tmem = tmem_base + (as * 2 + px) * p.acs;
+                const int b = dx - px + 1;
+                const uint32_t d_tmem = tmem_base + (acc * 2 + px) * p.acs;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
-                  const uint64_t da = make_smem_desc(sa + ch * A_SUB, ROWB);
-                  const uint64_t db = make_smem_desc(sb + (s * NCH + ch) * b_sub, ROWB);
+                  // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
+                  const uint64_t da = make_desc_sbo(sa + ch * p.a_sub + (a * PW + dxi) * ROWB, ROWB, PW * ROWB);
+                  const uint32_t wb = RESB ? smem_u32(smem_b + ((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub)
+                                           : smem_u32(smem_b + bs_ * b_stage + (s * NCH + ch) * b_sub);
+                  const uint64_t db = make_smem_desc(wb, ROWB);
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
                     umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, started[px]);
@@ -142,30 +189,32 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                   }
                 }
               }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              if (!RESB) {
+                umma_commit(&bempty[bs_]);
+                if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
+              }
             }
-          }
+          umma_commit(&aempty[as_]);
+          if (++as_ == p.na) { as_ = 0; aph ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
-        if (++as == p.nacc) { as = 0; aphase ^= 1; }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == p.nacc) { acc = 0; tph ^= 1; }
       }
     }
   } else {
     const int quarter = warp % 4;
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int py = item & 1, t = item >> 1;
+    int acc = 0;
+    uint32_t tph = 0;
+    for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
       const int n = t / tiles_per_img, tr = t % tiles_per_img;
       const int yy = (tr / p.tiles_x) * TH + ty, xx = (tr % p.tiles_x) * TW + tx;
-      mbar_wait(&tfull_bar[as], aphase);
+      mbar_wait(&tfull_bar[acc], tph);
       tc_fence_after();
 #pragma unroll 1
       for (int px = 0; px < 2; ++px) {
         bf16* dst = p.out + (((long long)n * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px) * p.Cout;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (as * 2 + px) * p.acs;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * 2 + px) * p.acs;
         int c = 0;
         for (; c + 32 <= p.Cout; c += 32) {
           float v[32];
@@ -186,8 +235,8 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == p.nacc) { as = 0; aphase ^= 1; }
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == p.nacc) { acc = 0; tph ^= 1; }
     }
   }
   tc_fence_before();
@@ -198,13 +247,13 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
-template <int KC, int NCH>
+template <int KC, int NCH, bool RESB>
 void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   const int rowb = KC * 2;
   CUtensorMap mapA, mapB;
   uint64_t da[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.NB};
   uint64_t sa[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-  uint32_t ba[4] = {KC, TW, TH, 1};
+  uint32_t ba[4] = {KC, PW, PH, 1};
   uint64_t db[2] = {(uint64_t)4 * p.Cin, (uint64_t)4 * p.Cout};
   uint64_t sb[1] = {(uint64_t)4 * p.Cin * 2};
   uint32_t bb[2] = {KC, (uint32_t)p.Cout};
@@ -213,25 +262,40 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const int stage_bytes = NCH * BM * rowb + 2 * NCH * p.Cout * rowb;
-  p.stages = (200 * 1024) / stage_bytes;
-  if (p.stages > 8) p.stages = 8;
-  if (p.stages < 2) { c.fail(SJ_EUNSUPPORTED); return; }
-  size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
+  p.a_sub = (PH * PW * rowb + 1023) & ~1023;
+  p.a_slot = NCH * p.a_sub;
+  p.na = 3;
+  const int b_sub = p.Cout * rowb;
+  const int budget = 222 * 1024 - 1024 - 512;  // alignment slack + barriers
+  int b_bytes;
+  if (RESB) {
+    b_bytes = 8 * NCH * b_sub;
+    p.nbs = 1;
+  } else {
+    const int b_stage = 2 * NCH * b_sub;
+    p.nbs = (budget - p.na * p.a_slot) / b_stage;
+    if (p.nbs > MAX_STAGES) p.nbs = MAX_STAGES;
+    if (p.nbs < 2) { c.fail(SJ_EUNSUPPORTED); return; }
+    b_bytes = p.nbs * b_stage;
+  }
+  size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 512;
+  if (smem > 227 * 1024) { c.fail(SJ_EUNSUPPORTED); return; }
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
-  if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-  SJ_LAUNCH(c, "tc_upconv", (tc_upconv_kernel<KC, NCH>), grid, NTHREADS, smem, mapA, mapB, p);
+  int grid = num_sms() & ~1;  // even: CTA parity = output row phase
+  if (grid > 2 * p.num_tiles) grid = 2 * p.num_tiles;
+  SJ_LAUNCH(c, "tc_upconv", (tc_upconv_kernel<KC, NCH, RESB>), grid, NTHREADS, smem, mapA, mapB, p);
 }
 
 }  // namespace
 
 bool tc_upconv_supported(int H, int W, int Cin, int Cout) {
   if (H % TH || W % TW || Cout % 16 || Cout < 16 || Cout > 256) return false;
-  return Cin % 64 == 0 || Cin == 96;
+  if (Cin == 96) return 8 * 3 * Cout * 64 <= 100 * 1024;  // resident-weight variant
+  return Cin % 64 == 0;
 }
 
 // x bf16 [NB,H,W,Cin] -> y bf16 [NB,2H,2W,Cout]; w_tc = folded kernels [4][Cout][4*Cin] bf16
@@ -242,13 +306,13 @@ void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bi
   ConvP p{};
   p.NB = NB; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.tiles_x = W / TW; p.tiles_y = H / TH;
-  p.num_items = NB * p.tiles_x * p.tiles_y * 2;
+  p.num_tiles = NB * p.tiles_x * p.tiles_y;
   p.acs = (Cout + 63) / 64 * 64;
   p.nacc = 4 * p.acs <= 512 ? 2 : 1;
   p.bias = bias;
   p.out = (bf16*)y;
-  if (Cin % 64 == 0) launch_upconv<64, 1>(c, x, w_tc, p);
-  else launch_upconv<32, 3>(c, x, w_tc, p);
+  if (Cin == 96) launch_upconv<32, 3, true>(c, x, w_tc, p);   // 96 -> 48: weights resident (72 KB per row phase)
+  else launch_upconv<64, 1, false>(c, x, w_tc, p);
 }
 
 }  // namespace sj
