@@ -28,7 +28,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 2, BM = 128, NTHREADS = 192;
+constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 2, BM = 128, NTHREADS = 320;  // 2 + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 
 struct ConvP {
@@ -87,7 +87,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
@@ -150,6 +150,10 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, p.Cout);
+      constexpr uint32_t A_HI = desc_hi(ROWB, PW * ROWB), B_HI = desc_hi(ROWB, 8 * ROWB);
+      constexpr uint32_t A_SUB16 = (((PH * PW * ROWB) + 1023) & ~1023) >> 4;  // == p.a_sub >> 4
+      const uint32_t b_sub16 = (uint32_t)b_sub >> 4;
+      const uint32_t b_base_lo = desc_lo(smem_u32(smem_b));
       int as_ = 0, bs_ = 0, acc = 0;
       uint32_t aph = 0, bph = 0, tph = 0;
       if (RESB) {
@@ -159,33 +163,38 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
         mbar_wait(&tempty_bar[acc], tph ^ 1);
         tc_fence_after();
-        uint32_t started[2] = {0, 0};
+        const uint32_t d0 = tmem_base + (acc * 2) * p.acs, d1 = d0 + p.acs;
+        uint32_t st0 = 0, st1 = 0;
         for (int cg = 0; cg < groups; ++cg) {
           mbar_wait(&afull[as_], aph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + as_ * p.a_slot);
-          for (int a = 0; a < 2; ++a)
+          const uint32_t a_lo = desc_lo(smem_u32(smem_a + as_ * p.a_slot));
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+#pragma unroll
             for (int dxi = 0; dxi < 3; ++dxi) {
-              const int dx = dxi - 1, nb = dx == 0 ? 2 : 1;
+              uint32_t bstage_lo = 0;
               if (!RESB) {
                 mbar_wait(&bfull[bs_], bph);
                 tc_fence_after();
+                bstage_lo = b_base_lo + (uint32_t)bs_ * 2 * NCH * b_sub16;
               }
-              for (int s = 0; s < nb; ++s) {
-                const int px = dx < 0 ? 0 : (dx > 0 ? 1 : s);
-                const int b = dx - px + 1;
-                const uint32_t d_tmem = tmem_base + (acc * 2 + px) * p.acs;
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                if (dxi != 1 && s == 1) continue;  // dx = +-1 feeds a single column phase
+                const int px = dxi == 0 ? 0 : (dxi == 2 ? 1 : s);
+                const int b = dxi - px;  // column tap inside phase px
+                const uint32_t d_tmem = px ? d1 : d0;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                   // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
-                  const uint64_t da = make_desc_sbo(sa + ch * p.a_sub + (a * PW + dxi) * ROWB, ROWB, PW * ROWB);
-                  const uint32_t wb = RESB ? smem_u32(smem_b + ((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub)
-                                           : smem_u32(smem_b + bs_ * b_stage + (s * NCH + ch) * b_sub);
-                  const uint64_t db = make_smem_desc(wb, ROWB);
+                  const uint32_t va = a_lo + ch * A_SUB16 + (((a * PW + dxi) * ROWB) >> 4);
+                  const uint32_t vb = RESB ? b_base_lo + (uint32_t)((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub16
+                                           : bstage_lo + (uint32_t)(s * NCH + ch) * b_sub16;
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
-                    umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, started[px]);
-                    started[px] = 1;
+                    umma_bf16_w(d_tmem, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc, px ? st1 : st0);
+                    if (px) st1 = 1; else st0 = 1;
                   }
                 }
               }
@@ -194,6 +203,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
               }
             }
+          }
           umma_commit(&aempty[as_]);
           if (++as_ == p.na) { as_ = 0; aph ^= 1; }
         }
@@ -202,7 +212,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else {
-    const int quarter = warp % 4;
+    const int quarter = warp % 4, px = (warp - 2) / 4;  // warps 2..5 -> px 0, warps 6..9 -> px 1
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
     int acc = 0;
     uint32_t tph = 0;
@@ -211,8 +221,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int yy = (tr / p.tiles_x) * TH + ty, xx = (tr % p.tiles_x) * TW + tx;
       mbar_wait(&tfull_bar[acc], tph);
       tc_fence_after();
-#pragma unroll 1
-      for (int px = 0; px < 2; ++px) {
+      {
         bf16* dst = p.out + (((long long)n * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px) * p.Cout;
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * 2 + px) * p.acs;
         int c = 0;

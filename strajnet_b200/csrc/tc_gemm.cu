@@ -20,7 +20,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 192;
+constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int A_STAGE_BYTES_MAX = 256 * BK * 2;
 
 struct KParams {
@@ -70,7 +70,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
@@ -142,7 +142,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    const int quarter = warp % 4;
+    const int quarter = warp % 4, half = (warp - 2) / 4;  // two warps per TMEM lane quarter, each takes half the columns
+    const int csplit = ((p.BN / 16 + 1) / 2) * 16;
+    const int c_begin = half ? csplit : 0, c_end = half ? p.BN : csplit;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -189,14 +191,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           st8_bf16(p.C + crow * p.ldc + n + i, v + i);
         }
       };
-      int c = 0;
-      for (; c + 32 <= p.BN; c += 32) {
+      int c = c_begin;
+      for (; c + 32 <= c_end; c += 32) {
         float v[32];
         tmem_ld32(t_addr + c, v);
-#pragma unroll
-        for (int h = 0; h < 1; ++h) finish(v, n0 + c, 32);
+        finish(v, n0 + c, 32);
       }
-      if (c < p.BN) {
+      if (c < c_end) {
         float v[16];
         tmem_ld16(t_addr + c, v);
         finish(v, n0 + c, 16);
