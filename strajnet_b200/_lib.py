@@ -68,7 +68,7 @@ class SjTrajW(C.Structure):
 
 class SjDecoderW(C.Structure):
     _fields_ = [("upconv", SjLinear * 4), ("res", SjLinear * 2), ("res_f", SjLinear),
-                ("upconv_f", SjLinear * 2), ("out_w", c_fp), ("out_b", c_fp)]
+                ("upconv_f", SjLinear * 2), ("out_w", c_fp), ("out_b", c_fp), ("out_w_tc", c_fp)]
 
 
 class SjModelW(C.Structure):

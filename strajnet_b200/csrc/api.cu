@@ -388,7 +388,11 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
   { RoleScope r(c, "dec.upconvf0"); upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96); }
   void* f4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
   { RoleScope r(c, "dec.upconvf1"); upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48); }
-  { RoleScope r(c, "dec.outconv"); out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out); }
+  {
+    RoleScope r(c, "dec.outconv");
+    if (c.dtype == SJ_BF16 && w.out_w_tc) tc_out_conv(c, x4, f4, w.out_w_tc, w.out_b, B, out_layout, out);
+    else out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out);
+  }
   c.ws.release(mark);
 }
 

@@ -168,4 +168,8 @@ void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, con
 // crop the centre of x [B,P,P,C] -> y [B,P/2,P/2,C] (modules.py:614-622)
 void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
 
+// tcgen05 decoder head (tc_outconv.cu): bf16 inputs [B*8,256,256,48], fp32 logits out
+void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
+                 int out_layout, float* out);
+
 }  // namespace sj

@@ -1,0 +1,88 @@
+"""Pipelined inference: overlaps the host->device copy of batch i+1 and the device->host copy of
+batch i-1 with the forward of batch i, on three CUDA streams with double-buffered device slots.
+
+This is the call a serving user makes (the reference's `inference.py:186-214` loop copies one batch to
+the device, runs the model and pulls the logits back with `.numpy()`, serially):
+
+    pipe = InferencePipeline(model, batch=16)
+    for handle in pipe.run(iter_of_host_batches):     # or: h = pipe.submit(batch); ...; y = h.result()
+        logits = handle.result()                       # pinned host tensor [B,256,256,32] fp32
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator, List
+
+import torch
+
+_KEYS = ("ogm", "map_img", "obs", "occ", "flow")
+
+
+class Handle:
+    def __init__(self, event: torch.cuda.Event, host_out: torch.Tensor):
+        self._event, self._out = event, host_out
+
+    def result(self) -> torch.Tensor:
+        """Block until this batch's logits are in host memory and return them (valid until the slot is reused)."""
+        self._event.synchronize()
+        return self._out
+
+
+class InferencePipeline:
+    def __init__(self, model, batch: int, depth: int = 2):
+        self.model, self.B, self.depth = model, batch, depth
+        dev = model.device
+        S = model.cfg["input_size"][0]
+        shapes = {"ogm": (batch, S, S, 11, 2), "map_img": (batch, 256, 256, 3), "obs": (batch, 48, 11, 8),
+                  "occ": (batch, 16, 11, 8), "flow": (batch, S, S, 2)}
+        self.dev_in: List[Dict[str, torch.Tensor]] = [
+            {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in _KEYS} for _ in range(depth)]
+        self.dev_out = [torch.empty(batch, 256, 256, 32, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.host_out = [torch.empty(batch, 256, 256, 32, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]      # forward of slot done (inputs reusable)
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # logits of slot in host memory
+        self.i = 0
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.dev_in[0].values())
+        self.d2h_bytes = self.dev_out[0].numel() * 4
+        with torch.cuda.device(dev):
+            model.packed()  # weights on the device before the first submit
+            model._workspace(model.workspace_bytes(batch))
+            torch.cuda.synchronize(dev)  # weight uploads ran on the default stream
+
+    def submit(self, host_batch: Dict[str, torch.Tensor]) -> Handle:
+        """Enqueue one batch (host tensors, ideally pinned).  Returns immediately."""
+        s = self.i % self.depth
+        first_use = self.i < self.depth
+        self.i += 1
+        with torch.cuda.stream(self.s_in):
+            if not first_use:
+                self.s_in.wait_event(self.ev_run[s])  # the previous forward on this slot has consumed its inputs
+            for k in _KEYS:
+                self.dev_in[s][k].copy_(host_batch[k], non_blocking=True)
+            self.ev_in[s].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[s])
+            if not first_use:
+                self.s_run.wait_event(self.ev_out[s])  # the previous logits of this slot have left the device
+            d = self.dev_in[s]
+            self.model.forward_into(self.dev_out[s], d["ogm"], d["map_img"], d["obs"], d["occ"], d["flow"])
+            self.ev_run[s].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[s])
+            self.host_out[s].copy_(self.dev_out[s], non_blocking=True)
+            self.ev_out[s].record(self.s_out)
+        return Handle(self.ev_out[s], self.host_out[s])
+
+    def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[Handle]:
+        """Submit every batch, yielding the handle of batch i once batch i+depth-1 has been enqueued."""
+        pending: List[Handle] = []
+        for b in batches:
+            pending.append(self.submit(b))
+            if len(pending) >= self.depth:
+                yield pending.pop(0)
+        yield from pending
+
+    def synchronize(self) -> None:
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()

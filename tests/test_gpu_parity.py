@@ -285,3 +285,15 @@ def test_empty_and_bad_inputs(sj):
     z = {k: torch.zeros_like(v) for k, v in inp.items()}  # the reference's own dummy-zero build call
     ref = O.forward_from_inputs(oracle_model(), CFG256, z)
     assert max_abs(_fwd(m, z), ref) < FP32_TOL
+
+
+def test_inference_pipeline_matches_direct_call(sj):
+    """The pipelined serving API returns the same logits as a direct model call, for every batch in flight."""
+    from strajnet_b200.pipeline import InferencePipeline
+    m = _model(sj)
+    pipe = InferencePipeline(m, batch=2)
+    batches = [O.make_inputs(2, 256, seed=20 + i) for i in range(5)]
+    outs = [h.result().clone() for h in pipe.run({k: v.pin_memory() for k, v in b.items() if k != "mapt"} for b in batches)]
+    assert len(outs) == 5
+    for b, y in zip(batches, outs):
+        assert torch.equal(y, _fwd(m, b).cpu())
