@@ -59,6 +59,7 @@ typedef struct {
   SjNorm norm2;
   SjLinear fc1;           /* [C,4C] + [4C]            modules.py:36  */
   SjLinear fc2;           /* [4C,C] + [C]             modules.py:37  */
+  SjLinear qkv_ln;        /* qkv again, tensor-core copy with norm1 folded in (fused window-MSA kernel); w/b unused */
 } SjSwinBlockW;
 
 typedef struct { SjNorm norm; SjLinear reduction; } SjPatchMergeW; /* modules.py:265-292: LN(4C), [4C,2C] no bias */

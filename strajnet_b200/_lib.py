@@ -28,7 +28,7 @@ class SjNorm(C.Structure):
 
 class SjSwinBlockW(C.Structure):
     _fields_ = [("norm1", SjNorm), ("qkv", SjLinear), ("rpb_table", c_fp), ("proj", SjLinear),
-                ("norm2", SjNorm), ("fc1", SjLinear), ("fc2", SjLinear)]
+                ("norm2", SjNorm), ("fc1", SjLinear), ("fc2", SjLinear), ("qkv_ln", SjLinear)]
 
 
 class SjPatchMergeW(C.Structure):

@@ -1,6 +1,7 @@
 // C-ABI entry points (include/strajnet_b200.h) and the host-side sequencing of the forward path.
 // Every *_impl function mirrors one `call()` of the reference (file:line cited in the header).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -77,7 +78,13 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   void* x1 = c.alloc_act(M * C);
   void* hbuf = c.alloc_act(M * 4 * C);
 
-  if (c.dtype == SJ_BF16) {
+  static const bool fused_off = getenv("SJ_DISABLE_FUSED_WMSA") != nullptr;
+  const bool fused = c.dtype == SJ_BF16 && !fused_off && w.qkv_ln.w_tc && tc_wmsa_supported(B, H, W, C, heads, ws, shift);
+  if (fused) {
+    // K1: the whole attention half as one tcgen05 kernel (tc_wmsa.cu)
+    ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
+    tc_wmsa(c, x, x1, mean, rstd, w, B, H, W, shift);
+  } else if (c.dtype == SJ_BF16) {
     // tensor-core path: norm1 + roll + partition as one gather pass, then a plain GEMM
     layernorm_gather(c, x, x1, (int)M, C, w.norm1.g, w.norm1.b, 1e-5f, map, L);
     linear(c, x1, C, w.qkv, qkv, 3 * C, (int)M, 3 * C, C, ACT_NONE);
@@ -90,8 +97,8 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
     g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm1.g; g.ln_b = w.norm1.b;
     gemm(c, g);
   }
-  window_attn_core(c, qkv, o, w.rpb_table, (int)(M / 64), C, heads, shift > 0 ? 1 : 0, H, W, shift, nullptr, 0);
-  {  // proj -> window_reverse -> roll back -> + shortcut   (modules.py:132, :245-258)
+  if (!fused) window_attn_core(c, qkv, o, w.rpb_table, (int)(M / 64), C, heads, shift > 0 ? 1 : 0, H, W, shift, nullptr, 0);
+  if (!fused) {  // proj -> window_reverse -> roll back -> + shortcut   (modules.py:132, :245-258)
     GemmP g;
     g.A = o; g.lda = C; g.set_weights(w.proj); g.ldw = C; g.C = x1; g.ldc = C;
     g.M = (int)M; g.N = C; g.K = C;

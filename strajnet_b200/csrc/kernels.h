@@ -168,6 +168,12 @@ void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, con
 // crop the centre of x [B,P,P,C] -> y [B,P/2,P/2,C] (modules.py:614-622)
 void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
 
+// ---- K1: fused window-MSA on tcgen05 (tc_wmsa.cu), bf16, C = 96 / 3 heads / window 8 ----------------
+bool tc_wmsa_supported(int B, int H, int W, int C, int heads, int ws, int shift);
+// out[token] = x[token] + proj(window_attention(norm1(x)))  for x, out bf16 [B, H*W, 96]; mean/rstd = norm1 stats of x
+void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
+             int H, int W, int shift);
+
 // tcgen05 decoder head (tc_outconv.cu): bf16 inputs [B*8,256,256,48], fp32 logits out
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
                  int out_layout, float* out);

@@ -308,6 +308,9 @@ class Packer:
         s.fc1 = self.linear(self.get(p + "mlp.fc1.kernel"), self.get(p + "mlp.fc1.bias"),
                             ln=(self.get(p + "norm2.gamma"), self.get(p + "norm2.beta")))
         s.fc2 = self.linear(self.get(p + "mlp.fc2.kernel"), self.get(p + "mlp.fc2.bias"))
+        if self.tc:
+            s.qkv_ln = self.linear(self.get(p + "attn.qkv.kernel"), self.get(p + "attn.qkv.bias"),
+                                   ln=(self.get(p + "norm1.gamma"), self.get(p + "norm1.beta")))
         return s
 
     def patch_merge(self, p: str) -> L.SjPatchMergeW:
