@@ -136,7 +136,7 @@ typedef struct {
   SjLinear upconv_f[2]; /* 128->96, 96->48, ELU */
   const float* out_w;   /* [2][9*48,2]: output_layer then output_layer_f */
   const float* out_b;   /* [2][2] */
-  const void* out_w_tc; /* bf16 [2 heads x 16 rows][9 taps x 64]: row o<2 / channel c<48 = out_w[head][tap*48+c][o], rest 0; or NULL */
+  const void* out_w_tc; /* bf16 [2 heads][32 rows][64]: row tap*2+o (<18), channel c (<48) = out_w[head][tap*48+c][o], rest 0; or NULL */
 } SjDecoderW;
 
 typedef struct {

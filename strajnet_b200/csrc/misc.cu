@@ -66,12 +66,12 @@ __global__ void center_crop_kernel(const T* __restrict__ x, T* __restrict__ y, i
 }
 
 // ---------------------------------------------------------------- fused patch embedding (K3)
-constexpr int PE_TOK = 8;
+constexpr int PE_TOK = 16;
 constexpr int PE_KMAX = 16 * 11;
 
 template <typename T>
 __global__ void patch_embed_kernel(const PatchEmbedP p) {
-  __shared__ float ins[PE_TOK][PE_KMAX];
+  __shared__ __align__(16) float ins[PE_TOK][PE_KMAX];
   __shared__ float vals[PE_TOK][128];
   __shared__ float stat[PE_TOK][2];
   const int n = threadIdx.x, E = p.E;
@@ -128,10 +128,17 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
     for (int t = 0; t < PE_TOK; ++t) acc[t] = 0.f;
     if (n < E) {
       const float* w = p.w[in] + n;
-      for (int k = 0; k < K; ++k) {
-        float wv = w[(long long)k * E];
+      for (int k = 0; k < K; k += 4) {  // 4 weights per step, each reused for all PE_TOK tokens (broadcast LDS.128)
+        const float w0 = w[(long long)k * E], w1 = w[(long long)(k + 1) * E], w2 = w[(long long)(k + 2) * E],
+                    w3 = w[(long long)(k + 3) * E];
 #pragma unroll
-        for (int t = 0; t < PE_TOK; ++t) acc[t] = fmaf(ins[t][k], wv, acc[t]);
+        for (int t = 0; t < PE_TOK; ++t) {
+          const float4 x4 = *reinterpret_cast<const float4*>(&ins[t][k]);
+          acc[t] = fmaf(x4.x, w0, acc[t]);
+          acc[t] = fmaf(x4.y, w1, acc[t]);
+          acc[t] = fmaf(x4.z, w2, acc[t]);
+          acc[t] = fmaf(x4.w, w3, acc[t]);
+        }
       }
       float bv = p.bias[in][n];
 #pragma unroll
@@ -173,50 +180,77 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
 }
 
 // ---------------------------------------------------------------- FG-MSA offset network
-// one block (384 threads) per (b, pixel) of the 16x16 grid
+// one block (384 threads = output channels) per (b, image row i, 8-pixel half row): the grouped 3x3 conv
+// weights are read once per block and reused for the 8 pixels
+constexpr int FGP = 8;
 template <typename T>
 __global__ void __launch_bounds__(384) fg_offset_kernel(const T* __restrict__ q, int ldq, SjFgmsaW w,
                                                         float* __restrict__ off, float* __restrict__ pos) {
-  __shared__ float qs[9][384];
-  __shared__ float us[384];
-  __shared__ float red[12];
-  const int n = threadIdx.x, b = blockIdx.x / 256, pix = blockIdx.x % 256, i = pix / 16, j = pix % 16;
-  for (int tap = 0; tap < 9; ++tap) {
-    int yy = i + tap / 3 - 1, xx = j + tap % 3 - 1;
-    qs[tap][n] = (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) ? ldf<T>(q + ((long long)b * 256 + yy * 16 + xx) * ldq + n) : 0.f;
-  }
+  __shared__ __align__(16) float qs[3][FGP + 2][384];
+  float (*us)[384] = reinterpret_cast<float (*)[384]>(&qs[0][0][0]);  // aliases qs: dead after the conv
+  __shared__ float red[12][FGP];
+  __shared__ float stat[FGP][2];
+  const int n = threadIdx.x, b = blockIdx.x / 32, rem = blockIdx.x % 32, i = rem / 2, j0 = (rem % 2) * FGP;
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < FGP + 2; ++cc) {
+      int yy = i + r - 1, xx = j0 + cc - 1;
+      qs[r][cc][n] = (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) ? ldf<T>(q + ((long long)b * 256 + yy * 16 + xx) * ldq + n) : 0.f;
+    }
   __syncthreads();
   const int g = n / 48;
-  float acc = w.conv0_b[n];
+  float acc[FGP];
+#pragma unroll
+  for (int pz = 0; pz < FGP; ++pz) acc[pz] = w.conv0_b[n];
   for (int tap = 0; tap < 9; ++tap) {
     const float* wt = w.conv0_w + (long long)tap * 48 * 384 + n;
-    const float* qv = &qs[tap][g * 48];
-#pragma unroll 8
-    for (int cc = 0; cc < 48; ++cc) acc = fmaf(qv[cc], wt[cc * 384], acc);
+    const int r = tap / 3, dx = tap % 3;
+    for (int cc = 0; cc < 48; cc += 4) {
+      const float w0 = wt[cc * 384], w1 = wt[(cc + 1) * 384], w2 = wt[(cc + 2) * 384], w3 = wt[(cc + 3) * 384];
+#pragma unroll
+      for (int pz = 0; pz < FGP; ++pz) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&qs[r][pz + dx][g * 48 + cc]);
+        acc[pz] = fmaf(x4.x, w0, acc[pz]);
+        acc[pz] = fmaf(x4.y, w1, acc[pz]);
+        acc[pz] = fmaf(x4.z, w2, acc[pz]);
+        acc[pz] = fmaf(x4.w, w3, acc[pz]);
+      }
+    }
   }
   // LayerNorm over 384 channels, eps 1e-3 (Keras default), then tanh-GELU
   const int warp = n / 32, lane = n % 32;
-  float s = warp_sum(acc);
-  if (lane == 0) red[warp] = s;
+#pragma unroll
+  for (int pz = 0; pz < FGP; ++pz) {
+    float s = warp_sum(acc[pz]);
+    if (lane == 0) red[warp][pz] = s;
+  }
   __syncthreads();
-  float mu = 0.f;
-  for (int k = 0; k < 12; ++k) mu += red[k];
-  mu /= 384.f;
+  if (n < FGP) {
+    float mu = 0.f;
+    for (int k = 0; k < 12; ++k) mu += red[k][n];
+    stat[n][0] = mu / 384.f;
+  }
   __syncthreads();
-  float d = acc - mu;
-  float s2 = warp_sum(d * d);
-  if (lane == 0) red[warp] = s2;
+#pragma unroll
+  for (int pz = 0; pz < FGP; ++pz) {
+    float d = acc[pz] - stat[pz][0];
+    float s2 = warp_sum(d * d);
+    if (lane == 0) red[warp][pz] = s2;
+  }
   __syncthreads();
-  float var = 0.f;
-  for (int k = 0; k < 12; ++k) var += red[k];
-  var /= 384.f;
-  float u = d * rsqrtf(var + 1e-3f) * w.conv_norm.g[n] + w.conv_norm.b[n];
-  us[n] = gelu_tanh(u);
+  if (n < FGP) {
+    float var = 0.f;
+    for (int k = 0; k < 12; ++k) var += red[k][n];
+    stat[n][1] = rsqrtf(var / 384.f + 1e-3f);
+  }
   __syncthreads();
-  if (n < 16) {
-    int gg = n / 2, o = n % 2;
+  const float gam = w.conv_norm.g[n], bet = w.conv_norm.b[n];
+#pragma unroll
+  for (int pz = 0; pz < FGP; ++pz) us[pz][n] = gelu_tanh((acc[pz] - stat[pz][0]) * stat[pz][1] * gam + bet);
+  __syncthreads();
+  if (n < FGP * 16) {
+    const int pz = n / 16, gg = (n % 16) / 2, o = n % 2, j = j0 + pz, pix = i * 16 + j;
     float a = 0.f;
-    for (int cc = 0; cc < 48; ++cc) a = fmaf(us[gg * 48 + cc], w.offproj_w[cc * 2 + o], a);
+    for (int cc = 0; cc < 48; ++cc) a = fmaf(us[pz][gg * 48 + cc], w.offproj_w[cc * 2 + o], a);
     a = tanhf(a) * 8.0f;  // offset_range = (Hk/2, Wk/2) = (8, 8), FG_MSA.py:115-117
     long long idx = (((long long)b * 8 + gg) * 256 + pix) * 2 + o;
     off[idx] = a;
@@ -475,8 +509,8 @@ void patch_embed(Ctx& c, const PatchEmbedP& p) {
 
 void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {
   if (!c.ok() || c.dry) return;
-  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<bf16>, B * 256, 384, 0, (const bf16*)q, ldq, *w, off, pos);
-  else SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<float>, B * 256, 384, 0, (const float*)q, ldq, *w, off, pos);
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<bf16>, B * 32, 384, 0, (const bf16*)q, ldq, *w, off, pos);
+  else SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<float>, B * 32, 384, 0, (const float*)q, ldq, *w, off, pos);
 }
 void build_query(Ctx& c, const void* q2, const float* off, const SjFgmsaW* w, int B, int fg, void* query) {
   if (!c.ok() || c.dry) return;

@@ -435,11 +435,11 @@ class Packer:
         ko, kf = self.get(p + "output_layer.kernel"), self.get(p + "output_layer_f.kernel")
         s.out_w = self.ptr(torch.stack([ko.reshape(432, 2), kf.reshape(432, 2)], 0))
         s.out_b = self.ptr(torch.stack([self.get(p + "output_layer.bias"), self.get(p + "output_layer_f.bias")], 0))
-        if self.tc:  # [2 heads][16 rows][9 taps][64 ch], zero padded
-            wt = torch.zeros(2, 16, 9, 64)
+        if self.tc:  # pointwise projection [2 heads][32 rows = tap*2+o (18 real)][64 ch (48 real)], zero padded
+            wt = torch.zeros(2, 32, 64)
             for h, k in enumerate((ko, kf)):
-                wt[h, :2, :, :48] = k.reshape(9, 48, 2).permute(2, 0, 1)
-            s.out_w_tc = self.ptr(wt.reshape(32, 576), torch.bfloat16)
+                wt[h, :18, :48] = k.reshape(9, 48, 2).permute(0, 2, 1).reshape(18, 48)
+            s.out_w_tc = self.ptr(wt.reshape(64, 64), torch.bfloat16)
         return s
 
     def model(self, cfg: dict, fg_msa: bool, fg: bool, large_ogm: bool) -> L.SjModelW:
