@@ -107,20 +107,20 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
     const int Cin = p.Cin[in], es = p.es[in], S = p.S[in], K = 16 * Cin;
     const int pad = in == 1 ? p.pad1 : 0;
     __syncthreads();
-    for (int i = n; i < PE_TOK * K; i += blockDim.x) {
-      int t = i / K, k = i % K;
-      long long tok = tok0 + t;
-      float v = 0.f;
+    // gather: each (token, patch row) is one contiguous run of 4*Cin channels in the NHWC input; a warp takes
+    // a run, lanes stride over it (no per-element index arithmetic)
+    const int run = 4 * Cin;
+    for (int pr = warp; pr < PE_TOK * 4; pr += nwarps) {
+      const int t = pr >> 2, ky = pr & 3;
+      const long long tok = tok0 + t;
+      const float* src = nullptr;
       if (tok < ntok) {
-        int pj = tok % P, pi = (tok / P) % P, b = tok / ((long long)P * P);
-        pi -= pad;
-        pj -= pad;
-        if (pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4) {
-          int c = k % Cin, kx = (k / Cin) % 4, ky = k / (4 * Cin);
-          v = p.img[in][((((long long)b * S + 4 * pi + ky) * S + 4 * pj + kx) * Cin + c) * es];
-        }
+        const int pj = (int)(tok % P) - pad, pi = (int)((tok / P) % P) - pad;
+        const long long b = tok / ((long long)P * P);
+        if (pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4)
+          src = p.img[in] + (((b * S + 4 * pi + ky) * S + 4 * pj) * Cin) * es;
       }
-      ins[t][k] = v;
+      for (int j = lane; j < run; j += 32) ins[t][ky * run + j] = src ? src[(long long)j * es] : 0.f;
     }
     __syncthreads();
     float acc[PE_TOK];

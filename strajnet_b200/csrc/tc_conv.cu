@@ -37,6 +37,7 @@ struct ConvP {
   int acs;                  // TMEM column stride between accumulators
   int nacc;                 // accumulator stages (1 or 2)
   int na, nbs;              // A-patch slots, B stages (streaming mode)
+  int stack;                // dx = 0 tap as one N = 2*Cout MMA (accumulators adjacent: acs == Cout)
   int a_slot;               // bytes per A slot (all chunks of a group, each 1024-aligned)
   int a_sub;                // bytes per chunk sub-patch (padded to 1024)
   const float* bias;
@@ -74,6 +75,8 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tfull_bar = bars + 4 * MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(bars + 48);  // [Cout] (<= 256 floats), 16-byte aligned
+  for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) bias_s[i] = p.bias[i];
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -107,11 +110,13 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       if (RESB) {  // the 8 (px, a, b) tiles of this row phase, loaded once
         mbar_expect_tx(&bfull[0], 8 * NCH * b_sub);
-        for (int px = 0; px < 2; ++px)
-          for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2; ++b)
-              for (int ch = 0; ch < NCH; ++ch)
-                tma_load_2d(smem_b + ((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub, &mapB, &bfull[0],
+        // order [a][chunk][slot], slot = (px0,b0) (px0,b1) (px1,b0) (px1,b1): the two tiles of the dx = 0 tap
+        // (slots 1, 2) are adjacent, so one MMA with N = 2*Cout feeds both column phases
+        for (int a = 0; a < 2; ++a)
+          for (int ch = 0; ch < NCH; ++ch)
+            for (int px = 0; px < 2; ++px)
+              for (int b = 0; b < 2; ++b)
+                tma_load_2d(smem_b + (((a * NCH + ch) * 4) + px * 2 + b) * b_sub, &mapB, &bfull[0],
                             (a * 2 + b) * p.Cin + ch * KC, (py * 2 + px) * p.Cout);
       }
       int as_ = 0, bs_ = 0;
@@ -129,7 +134,8 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (++as_ == p.na) { as_ = 0; aph ^= 1; }
           if (!RESB) {
             for (int a = 0; a < 2; ++a)
-              for (int dxi = 0; dxi < 3; ++dxi) {
+              for (int di = 0; di < 3; ++di) {
+                const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);  // centre column tap first (see the MMA warp)
                 const int dx = dxi - 1, nb = dx == 0 ? 2 : 1;
                 mbar_wait(&bempty[bs_], bph ^ 1);
                 mbar_expect_tx(&bfull[bs_], nb * NCH * b_sub);
@@ -149,7 +155,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.Cout);
+      const uint32_t idesc = make_idesc_bf16(BM, p.Cout), idesc2 = make_idesc_bf16(BM, 2 * p.Cout);
       constexpr uint32_t A_HI = desc_hi(ROWB, PW * ROWB), B_HI = desc_hi(ROWB, 8 * ROWB);
       constexpr uint32_t A_SUB16 = (((PH * PW * ROWB) + 1023) & ~1023) >> 4;  // == p.a_sub >> 4
       const uint32_t b_sub16 = (uint32_t)b_sub >> 4;
@@ -172,16 +178,21 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
+            for (int di = 0; di < 3; ++di) {
+              // the centre column tap goes first: when stacked it initialises both accumulators with one flag
+              const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);
               uint32_t bstage_lo = 0;
               if (!RESB) {
                 mbar_wait(&bfull[bs_], bph);
                 tc_fence_after();
                 bstage_lo = b_base_lo + (uint32_t)bs_ * 2 * NCH * b_sub16;
               }
+              // dx = -1 -> phase px0 (tap b=0); dx = +1 -> px1 (b=1); dx = 0 -> px0 (b=1) and px1 (b=0), issued as
+              // ONE MMA over both accumulators when they are adjacent in TMEM (stack), halving the A re-reads
+              const bool stack = dxi == 1 && p.stack;
 #pragma unroll
               for (int s = 0; s < 2; ++s) {
-                if (dxi != 1 && s == 1) continue;  // dx = +-1 feeds a single column phase
+                if (s == 1 && (dxi != 1 || stack)) continue;
                 const int px = dxi == 0 ? 0 : (dxi == 2 ? 1 : s);
                 const int b = dxi - px;  // column tap inside phase px
                 const uint32_t d_tmem = px ? d1 : d0;
@@ -189,12 +200,19 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int ch = 0; ch < NCH; ++ch) {
                   // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
                   const uint32_t va = a_lo + ch * A_SUB16 + (((a * PW + dxi) * ROWB) >> 4);
-                  const uint32_t vb = RESB ? b_base_lo + (uint32_t)((((px * 2 + a) * 2 + b) * NCH) + ch) * b_sub16
+                  const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
                                            : bstage_lo + (uint32_t)(s * NCH + ch) * b_sub16;
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
-                    umma_bf16_w(d_tmem, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc, px ? st1 : st0);
-                    if (px) st1 = 1; else st0 = 1;
+                    if (stack) {
+                      umma_bf16_w(d0, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc2, st0);  // st0 == st1 here
+                      st0 = 1;
+                      st1 = 1;
+                    } else {
+                      umma_bf16_w(d_tmem, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc, px ? st1 : st0);
+                      if (px) st1 = 1;
+                      else st0 = 1;
+                    }
                   }
                 }
               }
@@ -229,7 +247,11 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           float v[32];
           tmem_ld32(t_addr + c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i] + p.bias[c + i], ACT_ELU);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+            v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
+            v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 8) st8_bf16(dst + c + i, v + i);
         }
@@ -237,7 +259,11 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           float v[16];
           tmem_ld16(t_addr + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i] + p.bias[c + i], ACT_ELU);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+            v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
+            v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
+          }
 #pragma unroll
           for (int i = 0; i < 16; i += 8) st8_bf16(dst + c + i, v + i);
         }
@@ -275,7 +301,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   p.a_slot = NCH * p.a_sub;
   p.na = 3;
   const int b_sub = p.Cout * rowb;
-  const int budget = 222 * 1024 - 1024 - 512;  // alignment slack + barriers
+  const int budget = 222 * 1024 - 1024 - 2048;  // alignment slack + barriers + bias
   int b_bytes;
   if (RESB) {
     b_bytes = 8 * NCH * b_sub;
@@ -287,7 +313,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
     if (p.nbs < 2) { c.fail(SJ_EUNSUPPORTED); return; }
     b_bytes = p.nbs * b_stage;
   }
-  size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 512;
+  size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 2048;  // barriers + bias
   if (smem > 227 * 1024) { c.fail(SJ_EUNSUPPORTED); return; }
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -316,7 +342,8 @@ void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bi
   p.NB = NB; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.tiles_x = W / TW; p.tiles_y = H / TH;
   p.num_tiles = NB * p.tiles_x * p.tiles_y;
-  p.acs = (Cout + 63) / 64 * 64;
+  p.stack = 2 * Cout <= 256 && Cout % 16 == 0;
+  p.acs = p.stack ? Cout : (Cout + 63) / 64 * 64;
   p.nacc = 4 * p.acs <= 512 ? 2 : 1;
   p.bias = bias;
   p.out = (bf16*)y;

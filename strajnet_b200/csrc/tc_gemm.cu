@@ -11,6 +11,7 @@
 // LayerNorm fold: LN(x).W + b == rstd*(x.(g*W) - mean*colsum(g*W)) + (beta.W + b), so the raw
 // activations go through TMA untouched and the per-row affine is applied in the epilogue.
 #include <cstdio>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -45,6 +46,8 @@ struct KParams {
   int dbg_bo;     // probe: set the descriptor base_offset field from the start address
 };
 
+// ACT / LN are compile-time so the fully unrolled epilogue stays small enough for the instruction caches
+template <int ACT, bool LN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -160,7 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (p.cm.inner > 0) crow = (long long)(m / p.cm.inner) * p.cm.outer + (m % p.cm.inner);
         crow += (long long)g * p.cm.gstride;
         if (p.cm.map) crow = (crow / p.cm.map_len) * p.cm.map_len + p.cm.map[crow % p.cm.map_len];
-        if (p.ln_mean) {
+        if (LN) {
           // LN statistics are indexed like the A rows
           long long arow = m;
           if (p.a_mode == 1) arow = ((long long)(m / p.a_inner) * p.groups + g) * p.a_inner + (m % p.a_inner);
@@ -169,39 +172,52 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
-      const float* lns = p.ln_s ? p.ln_s + (long long)g * p.ln_gstride : nullptr;
+      const float* lns = LN ? p.ln_s + (long long)g * p.ln_gstride : nullptr;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.BN;
-      auto finish = [&](float* v, int n, int cnt) {  // LN fold / bias / activation / residual / store, cnt columns
-        if (!valid) return;
-        for (int i = 0; i < cnt; ++i) {
-          float x = v[i];
-          if (lns) x = rstd * (x - mean * lns[n + i]);
-          if (bias) x += bias[n + i];
-          v[i] = act_fast(x, p.act);
-        }
-        for (int i = 0; i < cnt; i += 8) {
-          if (p.R) {
-            float r[8];
-            ld8_bf16(p.R + crow * p.ldr + n + i, r);
+      // residual rows are fetched BEFORE the TMEM load of the same columns so the global-memory latency overlaps
+      // the tcgen05.ld round trip; everything is fully unrolled so v[] / rr[] stay in registers
+      auto chunk = [&](auto cnt_tag, int c) {
+        constexpr int CNT = decltype(cnt_tag)::value;
+        const int n = n0 + c;
+        float v[CNT];
+        uint4 rr[CNT / 8];
+        if (valid && p.R) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[i + j] += r[j];
+          for (int i = 0; i < CNT / 8; ++i) rr[i] = *reinterpret_cast<const uint4*>(p.R + crow * p.ldr + n + 8 * i);
+        }
+        if constexpr (CNT == 32) tmem_ld32(t_addr + c, v);
+        else tmem_ld16(t_addr + c, v);
+        if (!valid) return;
+#pragma unroll
+        for (int i = 0; i < CNT; i += 4) {  // 16-byte loads of the per-column vectors (L1-resident)
+          float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = l4;
+          if (LN) l4 = *reinterpret_cast<const float4*>(lns + n + i);
+          if (bias) b4 = *reinterpret_cast<const float4*>(bias + n + i);
+          if (LN) {
+            v[i] = rstd * (v[i] - mean * l4.x); v[i + 1] = rstd * (v[i + 1] - mean * l4.y);
+            v[i + 2] = rstd * (v[i + 2] - mean * l4.z); v[i + 3] = rstd * (v[i + 3] - mean * l4.w);
+          }
+          v[i] = act_fast(v[i] + b4.x, ACT); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT);
+          v[i + 2] = act_fast(v[i + 2] + b4.z, ACT); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT);
+        }
+#pragma unroll
+        for (int i = 0; i < CNT; i += 8) {
+          if (p.R) {
+            const uint32_t w[4] = {rr[i / 8].x, rr[i / 8].y, rr[i / 8].z, rr[i / 8].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[i + 2 * j] += __uint_as_float(w[j] << 16);
+              v[i + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
           }
           st8_bf16(p.C + crow * p.ldc + n + i, v + i);
         }
       };
       int c = c_begin;
-      for (; c + 32 <= c_end; c += 32) {
-        float v[32];
-        tmem_ld32(t_addr + c, v);
-        finish(v, n0 + c, 32);
-      }
-      if (c < c_end) {
-        float v[16];
-        tmem_ld16(t_addr + c, v);
-        finish(v, n0 + c, 16);
-      }
+      for (; c + 32 <= c_end; c += 32) chunk(std::integral_constant<int, 32>{}, c);
+      if (c < c_end) chunk(std::integral_constant<int, 16>{}, c);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -324,19 +340,24 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     return;
   }
   const size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      c.fail(SJ_ECUDA);
-      return;
-    }
-    attr_set = true;
-  }
   const int tiles = p.m_tiles * p.n_tiles * p.groups;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
-  SJ_LAUNCH(c, "tc_gemm", tc_gemm_kernel, grid, NTHREADS, smem_launch, mapA, mapB, p);
+  const bool ln = a.ln_mean != nullptr;
+#define SJ_TCG(ACT_, LN_)                                                                                             \
+  do {                                                                                                                \
+    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=  \
+        cudaSuccess) {                                                                                                \
+      c.fail(SJ_ECUDA);                                                                                               \
+      return;                                                                                                         \
+    }                                                                                                                 \
+    SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_>), grid, NTHREADS, smem_launch, mapA, mapB, p);                 \
+  } while (0)
+  if (a.act == ACT_GELU) { if (ln) SJ_TCG(ACT_GELU, true); else SJ_TCG(ACT_GELU, false); }
+  else if (a.act == ACT_ELU) { if (ln) SJ_TCG(ACT_ELU, true); else SJ_TCG(ACT_ELU, false); }
+  else { if (ln) SJ_TCG(ACT_NONE, true); else SJ_TCG(ACT_NONE, false); }
+#undef SJ_TCG
 }
 
 // ---- dispatcher ------------------------------------------------------------------------------------
