@@ -28,7 +28,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 2, BM = 128, NTHREADS = 320;  // 2 + 8 epilogue warps
+constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 2, BM = 128;
+constexpr int NTHREADS = 352;  // warp 0 TMA, warps 1 and 10 MMA issuers (one per column phase), warps 2..9 epilogue
 constexpr int MAX_STAGES = 8;
 
 struct ConvP {
@@ -56,12 +57,17 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t addr, uint32_t row_by
 
 // KC: channels per swizzled smem row (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NCH: chunks per A slot;
 // RESB: weights of this CTA's row phase resident in shared memory
-template <int KC, int NCH, bool RESB>
+// A128: the activation patch is staged in 64-channel SWIZZLE_128B chunks (fewer, wider TMA rows) even when the weights use
+// 32-channel chunks; channels past Cin are zero-filled by TMA and their K steps are skipped
+template <int KC, int NCH, bool RESB, bool A128>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int ROWB = KC * 2;
+  constexpr int ROWB = KC * 2;                    // weight tile row bytes
+  constexpr int AKC = A128 ? 64 : KC;             // channels per activation chunk
+  constexpr int AROWB = AKC * 2;
+  constexpr int ANCH = (NCH * KC + AKC - 1) / AKC;  // activation chunks per slot
   const int b_sub = p.Cout * ROWB;            // one weight tile: Cout rows x one chunk
   const int b_stage = 2 * NCH * b_sub;        // streaming: up to two phases per tap
   uint8_t* smem_a = smem;
@@ -84,12 +90,12 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     prefetch_tmap(&mapB);
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&afull[s], 1);
-      mbar_init(&aempty[s], 1);
+      mbar_init(&aempty[s], 2);  // one tcgen05.commit per MMA-issuing warp
       mbar_init(&bfull[s], 1);
-      mbar_init(&bempty[s], 1);
+      mbar_init(&bempty[s], 2);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tfull_bar[a], 2);
       mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
@@ -126,10 +132,10 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;
         for (int cg = 0; cg < groups; ++cg) {
           mbar_wait(&aempty[as_], aph ^ 1);
-          mbar_expect_tx(&afull[as_], NCH * PH * PW * ROWB);
+          mbar_expect_tx(&afull[as_], ANCH * PH * PW * AROWB);
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            tma_load_4d(smem_a + as_ * p.a_slot + ch * p.a_sub, &mapA, &afull[as_], (cg * NCH + ch) * KC, x0 - 1,
+          for (int ch = 0; ch < ANCH; ++ch)
+            tma_load_4d(smem_a + as_ * p.a_slot + ch * p.a_sub, &mapA, &afull[as_], cg * NCH * KC + ch * AKC, x0 - 1,
                         y0 - 1 + py, n);
           if (++as_ == p.na) { as_ = 0; aph ^= 1; }
           if (!RESB) {
@@ -153,11 +159,15 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
+    // Two MMA-issuing warps, one per column phase px (independent TMEM accumulators).  The single issuing thread
+    // spends ~20 scalar instructions per tcgen05.mma, which at N = 48..96 costs more than the MMA itself; two
+    // issuers halve that serial chain.  Each commits to the same mbarriers (arrival count 2).
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.Cout), idesc2 = make_idesc_bf16(BM, 2 * p.Cout);
-      constexpr uint32_t A_HI = desc_hi(ROWB, PW * ROWB), B_HI = desc_hi(ROWB, 8 * ROWB);
-      constexpr uint32_t A_SUB16 = (((PH * PW * ROWB) + 1023) & ~1023) >> 4;  // == p.a_sub >> 4
+      const int px = warp == 1 ? 0 : 1;
+      const uint32_t idesc = make_idesc_bf16(BM, p.Cout);
+      constexpr uint32_t A_HI = desc_hi(AROWB, PW * AROWB), B_HI = desc_hi(ROWB, 8 * ROWB);
+      constexpr uint32_t A_SUB16 = (((PH * PW * AROWB) + 1023) & ~1023) >> 4;  // == p.a_sub >> 4
       const uint32_t b_sub16 = (uint32_t)b_sub >> 4;
       const uint32_t b_base_lo = desc_lo(smem_u32(smem_b));
       int as_ = 0, bs_ = 0, acc = 0;
@@ -169,8 +179,8 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
         mbar_wait(&tempty_bar[acc], tph ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (acc * 2) * p.acs, d1 = d0 + p.acs;
-        uint32_t st0 = 0, st1 = 0;
+        const uint32_t d_tmem = tmem_base + (acc * 2 + px) * p.acs;
+        uint32_t started = 0;
         for (int cg = 0; cg < groups; ++cg) {
           mbar_wait(&afull[as_], aph);
           tc_fence_after();
@@ -179,40 +189,30 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int a = 0; a < 2; ++a) {
 #pragma unroll
             for (int di = 0; di < 3; ++di) {
-              // the centre column tap goes first: when stacked it initialises both accumulators with one flag
-              const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);
+              const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);  // same stage order as the producer
               uint32_t bstage_lo = 0;
               if (!RESB) {
                 mbar_wait(&bfull[bs_], bph);
                 tc_fence_after();
                 bstage_lo = b_base_lo + (uint32_t)bs_ * 2 * NCH * b_sub16;
               }
-              // dx = -1 -> phase px0 (tap b=0); dx = +1 -> px1 (b=1); dx = 0 -> px0 (b=1) and px1 (b=0), issued as
-              // ONE MMA over both accumulators when they are adjacent in TMEM (stack), halving the A re-reads
-              const bool stack = dxi == 1 && p.stack;
-#pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                if (s == 1 && (dxi != 1 || stack)) continue;
-                const int px = dxi == 0 ? 0 : (dxi == 2 ? 1 : s);
-                const int b = dxi - px;  // column tap inside phase px
-                const uint32_t d_tmem = px ? d1 : d0;
+              // column tap dx = dxi-1 feeds phase px iff b = dxi - px is 0 or 1; in a streamed stage the tile of px1 is
+              // slot 1 only for the shared centre tap
+              const int b = dxi - px;
+              if (b == 0 || b == 1) {
+                const int sl = (dxi == 1 && px == 1) ? 1 : 0;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                   // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
-                  const uint32_t va = a_lo + ch * A_SUB16 + (((a * PW + dxi) * ROWB) >> 4);
+                  const uint32_t view = a_lo + (((a * PW + dxi) * AROWB) >> 4);
                   const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
-                                           : bstage_lo + (uint32_t)(s * NCH + ch) * b_sub16;
+                                           : bstage_lo + (uint32_t)(sl * NCH + ch) * b_sub16;
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
-                    if (stack) {
-                      umma_bf16_w(d0, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc2, st0);  // st0 == st1 here
-                      st0 = 1;
-                      st1 = 1;
-                    } else {
-                      umma_bf16_w(d_tmem, va + 2 * k, A_HI, vb + 2 * k, B_HI, idesc, px ? st1 : st0);
-                      if (px) st1 = 1;
-                      else st0 = 1;
-                    }
+                    const int kk = ch * (KC / 16) + k;  // K step (16 channels) within the slot
+                    const uint32_t va = view + (kk / (AKC / 16)) * A_SUB16 + 2 * (kk % (AKC / 16));
+                    umma_bf16_w(d_tmem, va, A_HI, vb + 2 * k, B_HI, idesc, started);
+                    started = 1;
                   }
                 }
               }
@@ -282,23 +282,24 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
-template <int KC, int NCH, bool RESB>
+template <int KC, int NCH, bool RESB, bool A128>
 void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   const int rowb = KC * 2;
+  constexpr int AKC = A128 ? 64 : KC, ANCH = (NCH * KC + AKC - 1) / AKC;
   CUtensorMap mapA, mapB;
   uint64_t da[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.NB};
   uint64_t sa[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
-  uint32_t ba[4] = {KC, PW, PH, 1};
+  uint32_t ba[4] = {AKC, PW, PH, 1};
   uint64_t db[2] = {(uint64_t)4 * p.Cin, (uint64_t)4 * p.Cout};
   uint64_t sb[1] = {(uint64_t)4 * p.Cin * 2};
   uint32_t bb[2] = {KC, (uint32_t)p.Cout};
-  if (!encode_tmap(&mapA, x, 4, da, sa, ba, rowb) || !encode_tmap(&mapB, w_tc, 2, db, sb, bb, rowb)) {
+  if (!encode_tmap(&mapA, x, 4, da, sa, ba, AKC * 2) || !encode_tmap(&mapB, w_tc, 2, db, sb, bb, rowb)) {
     snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_upconv Cin=%d Cout=%d)", p.Cin, p.Cout);
     c.fail(SJ_ECUDA);
     return;
   }
-  p.a_sub = (PH * PW * rowb + 1023) & ~1023;
-  p.a_slot = NCH * p.a_sub;
+  p.a_sub = (PH * PW * AKC * 2 + 1023) & ~1023;
+  p.a_slot = ANCH * p.a_sub;
   p.na = 3;
   const int b_sub = p.Cout * rowb;
   const int budget = 222 * 1024 - 1024 - 2048;  // alignment slack + barriers + bias
@@ -316,13 +317,13 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 2048;  // barriers + bias
   if (smem > 227 * 1024) { c.fail(SJ_EUNSUPPORTED); return; }
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
-  if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH, RESB, A128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     c.fail(SJ_ECUDA);
     return;
   }
   int grid = num_sms() & ~1;  // even: CTA parity = output row phase
   if (grid > 2 * p.num_tiles) grid = 2 * p.num_tiles;
-  SJ_LAUNCH(c, "tc_upconv", (tc_upconv_kernel<KC, NCH, RESB>), grid, NTHREADS, smem, mapA, mapB, p);
+  SJ_LAUNCH(c, "tc_upconv", (tc_upconv_kernel<KC, NCH, RESB, A128>), grid, NTHREADS, smem, mapA, mapB, p);
 }
 
 }  // namespace
@@ -342,13 +343,13 @@ void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bi
   p.NB = NB; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.tiles_x = W / TW; p.tiles_y = H / TH;
   p.num_tiles = NB * p.tiles_x * p.tiles_y;
-  p.stack = 2 * Cout <= 256 && Cout % 16 == 0;
-  p.acs = p.stack ? Cout : (Cout + 63) / 64 * 64;
+  p.stack = 0;  // (one MMA warp per column phase now; the stacked centre-tap MMA is no longer used)
+  p.acs = (Cout + 63) / 64 * 64;
   p.nacc = 4 * p.acs <= 512 ? 2 : 1;
   p.bias = bias;
   p.out = (bf16*)y;
-  if (Cin == 96) launch_upconv<32, 3, true>(c, x, w_tc, p);   // 96 -> 48: weights resident (72 KB per row phase)
-  else launch_upconv<64, 1, false>(c, x, w_tc, p);
+  if (Cin == 96) launch_upconv<32, 3, true, true>(c, x, w_tc, p);   // 96 -> 48: weights resident (72 KB per row phase)
+  else launch_upconv<64, 1, false, false>(c, x, w_tc, p);
 }
 
 }  // namespace sj
