@@ -247,6 +247,17 @@ int sj_decoder_fwd(const void* x, const void* flow_res, const void* res0, const 
                    const SjDecoderW* w, int B, int out_layout, int dtype, void* workspace, size_t workspace_bytes,
                    sj_stream_t stream);
 
+/* Raw I/O of the serving loop.  Inputs as the reference's record decode holds them before the
+ * float casts (inference.py:91-93): ogm bool bytes [B,S,S,11,2] (SJ_IN_U8: nonzero -> 1.0), map int8 [B,256,256,3]
+ * (SJ_IN_I8_DIV256: value/256).  out_mode 1 fuses the submission quantisation (inference.py:124-136,160-182) into the
+ * decoder head: out is uint8 [B,256,256,32], channel k*4+{0,1} = round(sigmoid(logit)*255) as uint8, k*4+{2,3} =
+ * clip(round(flow),-128,127) as int8. */
+typedef enum { SJ_IN_F32 = 0, SJ_IN_U8 = 1, SJ_IN_I8_DIV256 = 2 } SjInputType;
+typedef struct { int ogm_type; int map_type; int out_mode; } SjIoSpec;
+int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, const float* obs, const float* occ,
+                       void* out, const SjModelW* w, const SjIoSpec* io, int B, int S, int dtype, void* workspace,
+                       size_t workspace_bytes, sj_stream_t stream);
+
 /* STrajNet.call, modules.py:815-839: -> out fp32 [B,256,256,32] */
 size_t sj_strajnet_workspace_bytes(int B, int S, int dtype);
 int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, const float* obs, const float* occ,

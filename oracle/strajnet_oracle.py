@@ -669,3 +669,20 @@ def make_inputs(B: int, S: int = 256, seed: int = 0, dtype=torch.float32) -> Dic
 
 def forward_from_inputs(w: Weights, cfg: dict, inp: Dict[str, Tensor], **kw):
     return strajnet_forward(w, cfg, inp["ogm"], inp["map_img"], inp["obs"], inp["occ"], inp["flow"], **kw)
+
+
+# --------------------------------------------------------------------------
+# serving-loop I/O around the model (inference.py:84-96, :124-136, :160-182)
+# --------------------------------------------------------------------------
+def decode_raw_inputs(ogm_bool: Tensor, map_int8: Tensor) -> Tuple[Tensor, Tensor]:
+    """inference.py:91,93: ogm bool bytes -> float32; map int8 -> float32 / 256."""
+    return (ogm_bool != 0).to(torch.float32), map_int8.to(torch.float32) / 256
+
+
+def quantize_outputs(y: Tensor) -> Tensor:
+    """inference.py:124-136 + :160-182 on the packed [B,256,256,32] logits -> uint8 [B,256,256,32]:
+    channels k*4+{0,1}: round(sigmoid(x)*255) as uint8; k*4+{2,3}: clip(round(x),-128,127) as int8 (two's complement)."""
+    y = y.to(torch.float32).reshape(*y.shape[:-1], 8, 4)
+    occ = torch.round(torch.sigmoid(y[..., :2]) * 255).to(torch.uint8)
+    flw = torch.clamp(torch.round(y[..., 2:]), -128, 127).to(torch.int8).view(torch.uint8)
+    return torch.cat([occ, flw], dim=-1).reshape(*y.shape[:-2], 32)

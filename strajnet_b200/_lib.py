@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libstrajnet_b200.so")
 
 SJ_F32, SJ_BF16 = 0, 1
+SJ_IN_F32, SJ_IN_U8, SJ_IN_I8_DIV256 = 0, 1, 2
 SJ_OK, SJ_EINVAL, SJ_EUNSUPPORTED, SJ_ECUDA, SJ_EWORKSPACE = 0, -1, -2, -3, -4
 
 c_fp = C.c_void_p  # device pointers travel as plain addresses
@@ -71,6 +72,10 @@ class SjDecoderW(C.Structure):
                 ("upconv_f", SjLinear * 2), ("out_w", c_fp), ("out_b", c_fp), ("out_w_tc", c_fp)]
 
 
+class SjIoSpec(C.Structure):
+    _fields_ = [("ogm_type", C.c_int), ("map_type", C.c_int), ("out_mode", C.c_int)]
+
+
 class SjModelW(C.Structure):
     _fields_ = [("encoder", SjEncoderW), ("fgmsa", SjFgmsaW), ("traj", SjTrajW), ("decoder", SjDecoderW),
                 ("fg_msa", C.c_int), ("fg", C.c_int), ("large_ogm", C.c_int)]
@@ -114,6 +119,7 @@ SIGNATURES = {
     "sj_decoder_workspace_bytes": (_sz, [_i, _i]),
     "sj_decoder_fwd": (_i, [_p, _p, _p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sj_strajnet_fwd_io": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), C.POINTER(SjIoSpec), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_fwd": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), _i, _i, _i, _p, _sz, _p]),
 }
 

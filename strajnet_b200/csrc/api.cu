@@ -163,8 +163,9 @@ void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBa
 }
 
 // ---- SwinTransformerEncoder.forward_features (modules.py:570-624) -------------------------------
-void encoder_impl(Ctx& c, const float* ogm, const float* map_img, const float* flow, void* flow_res, void* res0,
-                  void* res1, void* res2, const SjEncoderW& w, int B, int S, int large) {
+void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flow, void* flow_res, void* res0,
+                  void* res1, void* res2, const SjEncoderW& w, int B, int S, int large, int ogm_type = IN_F32,
+                  int map_type = IN_F32) {
   if (w.num_layers != 3 || w.window_size != 8 || w.embed_dim != 96) { c.fail(SJ_EUNSUPPORTED); return; }
   if ((large && S != 512) || (!large && S != 256)) { c.fail(SJ_EUNSUPPORTED); return; }  // Q13
   const int E = w.embed_dim, P = S / 4;
@@ -191,9 +192,9 @@ void encoder_impl(Ctx& c, const float* ogm, const float* map_img, const float* f
   void* x0 = f0;  // f0 is dead once the flow layer has run
   {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
     PatchEmbedP p;
-    p.img[0] = ogm; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
+    p.img[0] = ogm; p.itype[0] = ogm_type; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
     p.w[0] = w.pe_vec.proj.w; p.bias[0] = w.pe_vec.proj.b; p.g[0] = w.pe_vec.norm.g; p.b[0] = w.pe_vec.norm.b;
-    p.img[1] = map_img; p.Cin[1] = 3; p.es[1] = 1; p.S[1] = 256;
+    p.img[1] = map_img; p.itype[1] = map_type; p.Cin[1] = 3; p.es[1] = 1; p.S[1] = 256;
     p.w[1] = w.pe_map.proj.w; p.bias[1] = w.pe_map.proj.b; p.g[1] = w.pe_map.norm.g; p.b[1] = w.pe_map.norm.b;
     p.n_in = 2; p.pad1 = large ? 32 : 0;
     p.gf = w.all_patch_norm.g; p.bf = w.all_patch_norm.b; p.y = x0; p.B = B; p.E = E;
@@ -374,7 +375,7 @@ void res_add(Ctx& c, const void* skip, const SjLinear& w, const void* src, void*
   gemm(c, g);
 }
 
-void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0, const void* res1, float* out,
+void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0, const void* res1, void* out,
                   const SjDecoderW& w, int B, int out_layout) {
   const int NB = B * 8;
   size_t mark = c.ws.mark();
@@ -404,8 +405,8 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
 }
 
 // ---- STrajNet.call (modules.py:815-839) ----------------------------------------------------------
-void strajnet_impl(Ctx& c, const float* ogm, const float* map_img, const float* flow, const float* obs,
-                   const float* occ, float* out, const SjModelW& w, int B, int S) {
+void strajnet_impl(Ctx& c, const void* ogm, const void* map_img, const float* flow, const float* obs,
+                   const float* occ, void* out, const SjModelW& w, int B, int S, const SjIoSpec& io) {
   size_t mark = c.ws.mark();
   void* flow_res = c.alloc_act((size_t)B * 4096 * 96);
   void* res0 = c.alloc_act((size_t)B * 4096 * 96);
@@ -413,7 +414,10 @@ void strajnet_impl(Ctx& c, const float* ogm, const float* map_img, const float* 
   void* res2 = c.alloc_act((size_t)B * 256 * 384);
   void* query = c.alloc_act((size_t)B * 2048 * 384);
   void* obs_value = c.alloc_act((size_t)B * 2048 * 384);
-  { RoleScope r(c, "enc"); encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm); }
+  {
+    RoleScope r(c, "enc");
+    encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm, io.ogm_type, io.map_type);
+  }
   const void* q2 = res2;
   float* off = nullptr;
   if (w.fg_msa) {
@@ -427,7 +431,7 @@ void strajnet_impl(Ctx& c, const float* ogm, const float* map_img, const float* 
   if (w.fg && !w.fg_msa) { c.fail(SJ_EINVAL); return; }
   build_query(c, q2, off, &w.fgmsa, B, w.fg, query);  // repeat x8 (+ flow_hidden), modules.py:827-831
   { RoleScope r(c, "traj"); traj_impl(c, query, obs, occ, obs_value, w.traj, B); }
-  decoder_impl(c, obs_value, flow_res, res0, res1, out, w.decoder, B, 1);
+  decoder_impl(c, obs_value, flow_res, res0, res1, out, w.decoder, B, io.out_mode == 1 ? 2 : 1);
   c.ws.release(mark);
 }
 
@@ -768,14 +772,24 @@ size_t sj_strajnet_workspace_bytes(int B, int S, int dtype) {
   memset(&m, 0, sizeof(m));
   fake_encoder(m.encoder, zb);
   m.fg_msa = 1; m.fg = 1; m.large_ogm = (S == 512);
-  return measure(dtype, [&](Ctx& c) { strajnet_impl(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m, B, S); });
+  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0};
+  return measure(dtype, [&](Ctx& c) { strajnet_impl(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m, B, S, io); });
 }
+int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, const float* obs, const float* occ,
+                       void* out, const SjModelW* w, const SjIoSpec* io, int B, int S, int dtype, void* workspace,
+                       size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(ogm && map_img && flow && obs && occ && out && w && io && B > 0);
+  SJ_REQUIRE((io->ogm_type == SJ_IN_F32 || io->ogm_type == SJ_IN_U8) &&
+             (io->map_type == SJ_IN_F32 || io->map_type == SJ_IN_I8_DIV256) && (io->out_mode == 0 || io->out_mode == 1));
+  return run(workspace, workspace_bytes, dtype, stream,
+             [&](Ctx& c) { strajnet_impl(c, ogm, map_img, flow, obs, occ, out, *w, B, S, *io); });
+}
+
 int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, const float* obs, const float* occ,
                     float* out, const SjModelW* w, int B, int S, int dtype, void* workspace, size_t workspace_bytes,
                     sj_stream_t stream) {
-  SJ_REQUIRE(ogm && map_img && flow && obs && occ && out && w && B > 0);
-  return run(workspace, workspace_bytes, dtype, stream,
-             [&](Ctx& c) { strajnet_impl(c, ogm, map_img, flow, obs, occ, out, *w, B, S); });
+  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0};
+  return sj_strajnet_fwd_io(ogm, map_img, flow, obs, occ, out, w, &io, B, S, dtype, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -140,6 +140,22 @@ __host__ __device__ __forceinline__ int shift_region_id(int H, int W, int ws, in
   return by * 3 + bx;
 }
 
+// Submission quantisation of one waypoint (inference.py:124-136, :160-182): occupancy logits -> sigmoid ->
+// round(p*255) as uint8; flow -> clip(round(f), -128, 127) as int8 (np.round = round-half-even = rint).
+__device__ __forceinline__ uint32_t quantize_waypoint(float obs, float occ, float fx, float fy) {
+  const float po = 1.0f / (1.0f + expf(-obs)), pc = 1.0f / (1.0f + expf(-occ));
+  const uint32_t qo = (uint32_t)__float2int_rn(po * 255.0f), qc = (uint32_t)__float2int_rn(pc * 255.0f);
+  const int ix = max(-128, min(127, __float2int_rn(fx))), iy = max(-128, min(127, __float2int_rn(fy)));
+  return qo | (qc << 8) | ((uint32_t)(ix & 0xff) << 16) | ((uint32_t)(iy & 0xff) << 24);
+}
+// raw model inputs as the reference's record decode produces them (inference.py:91-93)
+enum InType { IN_F32 = 0, IN_U8 = 1, IN_I8_DIV256 = 2 };
+__device__ __forceinline__ float load_input(const void* base, long long idx, int type) {
+  if (type == IN_U8) return reinterpret_cast<const uint8_t*>(base)[idx] != 0 ? 1.0f : 0.0f;  // bool raster -> float
+  if (type == IN_I8_DIV256) return (float)reinterpret_cast<const int8_t*>(base)[idx] / 256.0f;  // int8 / 256
+  return reinterpret_cast<const float*>(base)[idx];
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace sj

@@ -133,7 +133,8 @@ void window_permute(Ctx& c, const void* x, void* y, int B, int H, int W, int C, 
 // Input i: fp32 [B,S_i,S_i,Cin_i] with channel element stride es_i.  The token grid is P x P with
 // P = S_0/4; input 1 may cover only the centre (pad1 > 0: tokens outside [pad1, P-pad1) get 0 from it).
 struct PatchEmbedP {
-  const float* img[2] = {nullptr, nullptr};
+  const void* img[2] = {nullptr, nullptr};
+  int itype[2] = {0, 0};  // InType of each input
   int Cin[2] = {0, 0}, es[2] = {1, 1}, S[2] = {0, 0};
   const float* w[2] = {nullptr, nullptr};   // [16*Cin, E]
   const float* bias[2] = {nullptr, nullptr};
@@ -163,8 +164,9 @@ void traj_prep(Ctx& c, const void* E, const int* cmask, const float* seg_w, int 
 void traj_final(Ctx& c, const void* E, const void* F2, const SjTrajW* w, int n_actors, void* key);
 
 // decoder head: two 3x3 48->2 convs (modules.py:767-770) written straight into the final layout
+// out_layout 0: fp32 [B,8,256,256,4]; 1: fp32 [B,256,256,32]; 2: quantised bytes [B,256,256,32] (quantize_waypoint)
 void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, const float* b, int B, int out_layout,
-              float* out);
+              void* out);
 // crop the centre of x [B,P,P,C] -> y [B,P/2,P/2,C] (modules.py:614-622)
 void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
 
@@ -176,6 +178,6 @@ void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* r
 
 // tcgen05 decoder head (tc_outconv.cu): bf16 inputs [B*8,256,256,48], fp32 logits out
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
-                 int out_layout, float* out);
+                 int out_layout, void* out);
 
 }  // namespace sj

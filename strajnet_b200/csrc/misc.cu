@@ -113,14 +113,14 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
     for (int pr = warp; pr < PE_TOK * 4; pr += nwarps) {
       const int t = pr >> 2, ky = pr & 3;
       const long long tok = tok0 + t;
-      const float* src = nullptr;
+      long long src = -1;  // element index of the run start
       if (tok < ntok) {
         const int pj = (int)(tok % P) - pad, pi = (int)((tok / P) % P) - pad;
         const long long b = tok / ((long long)P * P);
-        if (pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4)
-          src = p.img[in] + (((b * S + 4 * pi + ky) * S + 4 * pj) * Cin) * es;
+        if (pi >= 0 && pj >= 0 && pi < S / 4 && pj < S / 4) src = (((b * S + 4 * pi + ky) * S + 4 * pj) * Cin) * es;
       }
-      for (int j = lane; j < run; j += 32) ins[t][ky * run + j] = src ? src[(long long)j * es] : 0.f;
+      for (int j = lane; j < run; j += 32)
+        ins[t][ky * run + j] = src >= 0 ? load_input(p.img[in], src + (long long)j * es, p.itype[in]) : 0.f;
     }
     __syncthreads();
     float acc[PE_TOK];
@@ -387,7 +387,7 @@ constexpr int OC_TY = 16, OC_TX = 32, OC_PSTRIDE = 56;  // pixel stride in bf16 
 template <typename T>
 __global__ void __launch_bounds__(128) out_conv_kernel(const T* __restrict__ xo, const T* __restrict__ xf,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       int out_layout, float* __restrict__ out) {
+                                                       int out_layout, void* __restrict__ outv) {
   extern __shared__ __align__(16) uint8_t oc_smem[];
   T* tile = reinterpret_cast<T*>(oc_smem);                                                       // [18][34][56]
   float2* ws = reinterpret_cast<float2*>(oc_smem + (OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * sizeof(T));  // [2][432]
@@ -450,7 +450,15 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const T* __restrict__ xo,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int y = y0 + ty, x = x0 + tx + 8 * j;
-    if (out_layout == 1) {
+    float* out = reinterpret_cast<float*>(outv);
+    if (out_layout == 2) {
+      uint32_t q[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) q[t] = quantize_waypoint(acc[j][4 * t], acc[j][4 * t + 1], acc[j][4 * t + 2], acc[j][4 * t + 3]);
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outv) + (((long long)b * 256 + y) * 256 + x) * 32);
+      o[0] = make_uint4(q[0], q[1], q[2], q[3]);
+      o[1] = make_uint4(q[4], q[5], q[6], q[7]);
+    } else if (out_layout == 1) {
       float* o = out + (((long long)b * 256 + y) * 256 + x) * 32;
 #pragma unroll
       for (int k = 0; k < 32; k += 4)
@@ -548,7 +556,7 @@ void traj_final(Ctx& c, const void* E, const void* F2, const SjTrajW* w, int n_a
 }
 
 void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, const float* b, int B, int out_layout,
-              float* out) {
+              void* out) {
   if (!c.ok() || c.dry) return;
   dim3 grid(256 / OC_TX, 256 / OC_TY, B);
   const size_t smem = (size_t)(OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * c.esize() + 864 * sizeof(float2);

@@ -36,7 +36,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 256;
 struct OutP {
   int B, num_tiles, out_layout;
   const float* bias;  // [2][2]
-  float* out;
+  void* out;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -167,14 +167,22 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
         v[2 * th] = a0;
         v[2 * th + 1] = a1;
       }
-      if (p.out_layout == 1) {  // [B,256,256,32], channel = t*4 + head*2 + o
-        float4* o = reinterpret_cast<float4*>(p.out + (((long long)b * 256 + y) * 256 + x) * 32);
+      float* outf = reinterpret_cast<float*>(p.out);
+      if (p.out_layout == 2) {  // submission bytes (inference.py:160-182), 32 per pixel
+        uint32_t q[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) q[t] = quantize_waypoint(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (((long long)b * 256 + y) * 256 + x) * 32);
+        o[0] = make_uint4(q[0], q[1], q[2], q[3]);
+        o[1] = make_uint4(q[4], q[5], q[6], q[7]);
+      } else if (p.out_layout == 1) {  // [B,256,256,32], channel = t*4 + head*2 + o
+        float4* o = reinterpret_cast<float4*>(outf + (((long long)b * 256 + y) * 256 + x) * 32);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       } else {  // [B,8,256,256,4]
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          *reinterpret_cast<float4*>(p.out + ((((long long)b * 8 + t) * 256 + y) * 256 + x) * 4) =
+          *reinterpret_cast<float4*>(outf + ((((long long)b * 8 + t) * 256 + y) * 256 + x) * 4) =
               make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
       }
     }
@@ -192,7 +200,7 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
 // x_occ, x_flow: bf16 [B*8,256,256,48]; w_tc: bf16 [2 heads][32 rows = tap*2+o (18 real)][64 ch (48 real)];
 // bias fp32 [2][2]; out fp32
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
-                 int out_layout, float* out) {
+                 int out_layout, void* out) {
   if (!c.ok() || c.dry) return;
   CUtensorMap mapO, mapF, mapW;
   uint64_t da[4] = {48, 256, 256, (uint64_t)B * 8};

@@ -601,22 +601,49 @@ class STrajNet(Layer):
         return L.lib().sj_strajnet_workspace_bytes(B, self.cfg["input_size"][0], self.sj_dtype)
 
     def forward_into(self, out: Tensor, ogm: Tensor, map_img: Tensor, obs: Tensor, occ: Tensor, flow: Tensor) -> Tensor:
-        """Launch the forward on the current stream with caller-owned device buffers (graph-capturable)."""
+        """Launch the forward on the current stream with caller-owned device buffers (graph-capturable).
+
+        Raw I/O: `ogm` may be uint8/bool (the record's bool raster, inference.py:91), `map_img` int8
+        (decoded as value/256, inference.py:93); a uint8 `out` selects the fused submission quantisation
+        (inference.py:124-136,160-182) instead of fp32 logits."""
         B, S = ogm.shape[0], self.cfg["input_size"][0]
         lib = L.lib()
+        io = L.SjIoSpec()
+        io.ogm_type = L.SJ_IN_U8 if ogm.dtype in (torch.uint8, torch.bool) else L.SJ_IN_F32
+        io.map_type = L.SJ_IN_I8_DIV256 if map_img.dtype == torch.int8 else L.SJ_IN_F32
+        io.out_mode = 1 if out.dtype == torch.uint8 else 0
         ws, n = self._workspace(self.workspace_bytes(B))
-        L.check(lib.sj_strajnet_fwd(ogm.data_ptr(), map_img.data_ptr(), flow.data_ptr(), obs.data_ptr(), occ.data_ptr(),
-                                    out.data_ptr(), C.byref(self.packed()), B, S, self.sj_dtype, ws, n, _stream()),
-                "STrajNet")
+        L.check(lib.sj_strajnet_fwd_io(ogm.data_ptr(), map_img.data_ptr(), flow.data_ptr(), obs.data_ptr(), occ.data_ptr(),
+                                       out.data_ptr(), C.byref(self.packed()), C.byref(io), B, S, self.sj_dtype, ws, n,
+                                       _stream()), "STrajNet")
         return out
+
+    def _raw(self, x, shape, raw_dtypes):
+        t = torch.as_tensor(x)
+        if t.dtype in raw_dtypes:
+            t = t.to(device=self.device).contiguous()
+            if tuple(t.shape[1:]) != tuple(shape):
+                raise ValueError(f"input has shape {tuple(t.shape)}, expected [B,{','.join(map(str, shape))}]")
+            return t
+        return self._f32(t, shape)
+
+    def predict_quantized(self, ogm, map_img, obs, occ, flow) -> Tensor:
+        """Forward + the reference's submission quantisation (inference.py:124-136,160-182) in one pass:
+        uint8 [B,256,256,32]; channel k*4+{0,1}: round(sigmoid*255) (uint8), k*4+{2,3}: clip(round(flow)) (int8 bits)."""
+        S = self.cfg["input_size"][0]
+        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool))
+        map_img = self._raw(map_img, (256, 256, 3), (torch.int8,))
+        out = torch.empty(ogm.shape[0], 256, 256, 32, dtype=torch.uint8, device=self.device)
+        return self.forward_into(out, ogm, map_img, self._f32(obs, (48, 11, 8)), self._f32(occ, (16, 11, 8)),
+                                 self._f32(flow, (S, S, 2)))
 
     def call(self, ogm, map_img, training=True, obs=None, occ=None, mapt=None, flow=None, dense_vec=None, dense_map=None):
         _inference_only(training)
         if obs is None or occ is None or flow is None:
             raise ValueError("STrajNet: obs, occ and flow are required")
         S = self.cfg["input_size"][0]
-        ogm = self._f32(ogm, (S, S, 11, 2))
-        map_img = self._f32(map_img, (256, 256, 3))
+        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool))  # bool/uint8 rasters are consumed as they are
+        map_img = self._raw(map_img, (256, 256, 3), (torch.int8,))      # int8 map bytes are decoded as value/256
         flow = self._f32(flow, (S, S, 2))
         obs = self._f32(obs, (48, 11, 8))
         occ = self._f32(occ, (16, 11, 8))  # mapt is ignored (actor_only=True, modules.py:778)

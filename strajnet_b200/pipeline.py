@@ -28,23 +28,29 @@ class Handle:
 
 
 class InferencePipeline:
-    def __init__(self, model, batch: int, depth: int = 2):
+    def __init__(self, model, batch: int, depth: int = 2, raw_inputs: bool = False, quantized: bool = False):
+        """raw_inputs: ogm arrives as uint8/bool and map_img as int8 (the record's own types, inference.py:91-93);
+        quantized: results are the uint8 submission bytes (inference.py:160-182) instead of fp32 logits."""
         self.model, self.B, self.depth = model, batch, depth
         dev = model.device
         S = model.cfg["input_size"][0]
         shapes = {"ogm": (batch, S, S, 11, 2), "map_img": (batch, 256, 256, 3), "obs": (batch, 48, 11, 8),
                   "occ": (batch, 16, 11, 8), "flow": (batch, S, S, 2)}
+        dts = {k: torch.float32 for k in _KEYS}
+        if raw_inputs:
+            dts["ogm"], dts["map_img"] = torch.uint8, torch.int8
+        odt = torch.uint8 if quantized else torch.float32
         self.dev_in: List[Dict[str, torch.Tensor]] = [
-            {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in _KEYS} for _ in range(depth)]
-        self.dev_out = [torch.empty(batch, 256, 256, 32, dtype=torch.float32, device=dev) for _ in range(depth)]
-        self.host_out = [torch.empty(batch, 256, 256, 32, dtype=torch.float32).pin_memory() for _ in range(depth)]
+            {k: torch.empty(shapes[k], dtype=dts[k], device=dev) for k in _KEYS} for _ in range(depth)]
+        self.dev_out = [torch.empty(batch, 256, 256, 32, dtype=odt, device=dev) for _ in range(depth)]
+        self.host_out = [torch.empty(batch, 256, 256, 32, dtype=odt).pin_memory() for _ in range(depth)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]      # forward of slot done (inputs reusable)
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # logits of slot in host memory
         self.i = 0
-        self.h2d_bytes = sum(t.numel() * 4 for t in self.dev_in[0].values())
-        self.d2h_bytes = self.dev_out[0].numel() * 4
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.dev_in[0].values())
+        self.d2h_bytes = self.dev_out[0].numel() * self.dev_out[0].element_size()
         with torch.cuda.device(dev):
             model.packed()  # weights on the device before the first submit
             model._workspace(model.workspace_bytes(batch))
@@ -59,7 +65,10 @@ class InferencePipeline:
             if not first_use:
                 self.s_in.wait_event(self.ev_run[s])  # the previous forward on this slot has consumed its inputs
             for k in _KEYS:
-                self.dev_in[s][k].copy_(host_batch[k], non_blocking=True)
+                src = host_batch[k]
+                if src.dtype == torch.bool:
+                    src = src.view(torch.uint8)
+                self.dev_in[s][k].copy_(src, non_blocking=True)
             self.ev_in[s].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[s])

@@ -297,3 +297,61 @@ def test_inference_pipeline_matches_direct_call(sj):
     assert len(outs) == 5
     for b, y in zip(batches, outs):
         assert torch.equal(y, _fwd(m, b).cpu())
+
+
+def _raw_inputs(B, seed):
+    """The record's own types (inference.py:91-93): ogm bool bytes, map int8; plus their float decode."""
+    inp = O.make_inputs(B, 256, seed=seed)
+    ogm_u8 = (inp["ogm"] != 0).to(torch.uint8)
+    map_i8 = torch.round(inp["map_img"] * 256).to(torch.int8)
+    ogm_f, map_f = O.decode_raw_inputs(ogm_u8, map_i8)
+    assert torch.equal(ogm_f, inp["ogm"]) and torch.equal(map_f, inp["map_img"])
+    return inp, ogm_u8, map_i8
+
+
+def test_raw_typed_inputs_bit_identical(sj):
+    """f3: feeding bool/uint8 rasters and the int8 map directly equals feeding their float decode, bit for bit."""
+    m = _model(sj)
+    inp, ogm_u8, map_i8 = _raw_inputs(2, 31)
+    y_f = _fwd(m, inp)
+    y_r = m(ogm_u8, map_i8, training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
+    assert torch.equal(y_f, y_r)
+    y_b = m(ogm_u8.bool(), map_i8, training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
+    assert torch.equal(y_f, y_b)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_fused_submission_quantisation(sj, dtype):
+    """f1: the fused uint8/int8 epilogue equals the oracle's quantiser (inference.py:124-136,160-182) applied to the
+    same model's fp32 logits; rounding-boundary flips of one LSB are tolerated on < 0.1 % of the bytes."""
+    m = _model(sj, dtype=dtype)
+    inp, ogm_u8, map_i8 = _raw_inputs(2, 32)
+    logits = _fwd(m, inp).cpu()
+    q = m.predict_quantized(ogm_u8, map_i8, inp["obs"], inp["occ"], inp["flow"]).cpu()
+    ref = O.quantize_outputs(logits)
+    assert q.dtype == torch.uint8 and tuple(q.shape) == (2, 256, 256, 32)
+    # compare occupancy as uint8 and flow as int8
+    qa, ra = q.reshape(-1, 8, 4), ref.reshape(-1, 8, 4)
+    d_occ = (qa[..., :2].int() - ra[..., :2].int()).abs()
+    d_flw = (qa[..., 2:].view(torch.int8).int() - ra[..., 2:].view(torch.int8).int()).abs()
+    assert d_occ.max() <= 1 and d_flw.max() <= 1
+    frac = ((d_occ > 0).float().mean().item() + (d_flw > 0).float().mean().item()) / 2
+    print(f"{dtype}: fraction of bytes off by one LSB: {frac:.2e}")
+    assert frac < 1e-3
+    if dtype == "float32":  # and against the oracle's own logits
+        ref2 = O.quantize_outputs(O.forward_from_inputs(oracle_model(), CFG256, inp))
+        d2 = (q.reshape(-1, 8, 4)[..., :2].int() - ref2.reshape(-1, 8, 4)[..., :2].int()).abs()
+        assert d2.max() <= 1
+
+
+def test_pipeline_raw_quantised(sj):
+    from strajnet_b200.pipeline import InferencePipeline
+    m = _model(sj)
+    pipe = InferencePipeline(m, batch=2, raw_inputs=True, quantized=True)
+    inp, ogm_u8, map_i8 = _raw_inputs(2, 33)
+    host = dict(ogm=ogm_u8.pin_memory(), map_img=map_i8.pin_memory(), obs=inp["obs"].pin_memory(),
+                occ=inp["occ"].pin_memory(), flow=inp["flow"].pin_memory())
+    outs = [h.result().clone() for h in pipe.run(host for _ in range(3))]
+    ref = m.predict_quantized(ogm_u8, map_i8, inp["obs"], inp["occ"], inp["flow"]).cpu()
+    for y in outs:
+        assert torch.equal(y, ref)
