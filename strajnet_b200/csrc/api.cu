@@ -181,7 +181,25 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   }
   void* f0 = c.alloc_act(B * L0 * E);
   void* flow_x = c.alloc_act(B * L0 / 4 * 2 * E);
-  {  // patch_embed_flow -> flow_norm (modules.py:576-577)
+  // bf16 mode: the 4x4/s4 patch convs run as tcgen05 GEMMs over an im2col'ed bf16 matrix
+  const bool pe_tc = c.dtype == SJ_BF16 && w.pe_vec.proj.w_tc && w.pe_map.proj.w_tc && w.pe_flow.proj.w_tc;
+  auto embed_tc = [&](const void* img, int itype, int Simg, int Cin, int es, const SjPatchEmbedW& pw, void* conv_out) {
+    const int Kpad = (16 * Cin + 63) / 64 * 64;
+    const int Mtok = B * (Simg / 4) * (Simg / 4);
+    size_t mk = c.ws.mark();
+    void* A = c.alloc((size_t)Mtok * Kpad * 2);
+    im2col4(c, img, itype, B, Simg, Cin, es, Kpad, A);
+    TcGemmP t;
+    t.A = A; t.lda = Kpad; t.Bw = pw.proj.w_tc; t.M = Mtok; t.N = E; t.K = Kpad; t.bias = pw.proj.b; t.C = conv_out; t.ldc = E;
+    tc_gemm(c, t);
+    c.ws.release(mk);
+  };
+  if (pe_tc) {
+    void* cf = c.alloc_act(B * L0 * E);
+    embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
+    SjNorm none{};
+    pe_combine(c, cf, nullptr, B, P, 0, w.pe_flow.norm, none, w.flow_norm, f0);
+  } else {  // patch_embed_flow -> flow_norm (modules.py:576-577)
     PatchEmbedP p;
     p.img[0] = flow; p.Cin[0] = 2; p.es[0] = 1; p.S[0] = S;
     p.w[0] = w.pe_flow.proj.w; p.bias[0] = w.pe_flow.proj.b; p.g[0] = w.pe_flow.norm.g; p.b[0] = w.pe_flow.norm.b;
@@ -190,7 +208,13 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   }
   basic_layer_impl(c, f0, flow_x, full[0], w.flow_layer, nullptr, B, P, P, 8);
   void* x0 = f0;  // f0 is dead once the flow layer has run
-  {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
+  if (pe_tc) {
+    void* cv = c.alloc_act(B * L0 * E);
+    void* cm = c.alloc_act((size_t)B * 4096 * E);
+    embed_tc(ogm, ogm_type, S, 11, 2, w.pe_vec, cv);
+    embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
+    pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, x0);
+  } else {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
     PatchEmbedP p;
     p.img[0] = ogm; p.itype[0] = ogm_type; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
     p.w[0] = w.pe_vec.proj.w; p.bias[0] = w.pe_vec.proj.b; p.g[0] = w.pe_vec.norm.g; p.b[0] = w.pe_vec.norm.b;

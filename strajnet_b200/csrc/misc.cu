@@ -179,6 +179,73 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
   }
 }
 
+// ---------------------------------------------------------------- tensor-core patch embedding helpers (bf16 mode)
+// im2col of the 4x4/stride-4 patches into a bf16 matrix A[token][Kpad] (k = (ky*4+kx)*Cin + c, zero padded to Kpad),
+// so the conv becomes a plain tcgen05 GEMM.  One thread per 8 consecutive k (one 16-byte store).
+__global__ void im2col4_kernel(const void* __restrict__ img, int itype, int B, int S, int Cin, int es, int Kpad,
+                               bf16* __restrict__ A) {
+  const int k8n = Kpad / 8, P = S / 4, K = 16 * Cin;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * P * P * k8n) return;
+  const long long tok = i / k8n;
+  const int k0 = (int)(i % k8n) * 8;
+  const int pj = (int)(tok % P), pi = (int)((tok / P) % P);
+  const long long b = tok / ((long long)P * P);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    float x = 0.f;
+    if (k < K) {
+      const int c = k % Cin, kx = (k / Cin) & 3, ky = k / (4 * Cin);
+      x = load_input(img, ((((b * S + 4 * pi + ky) * S + 4 * pj + kx) * Cin) + c) * (long long)es, itype);
+    }
+    v[j] = x;
+  }
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+  u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+  *reinterpret_cast<uint4*>(A + tok * Kpad + k0) = u;
+}
+
+// y[token] = LN_f( LN_0(c0[token]) + LN_1(c1[token']) ) over E = 96 channels, eps 1e-5 (modules.py:445, :580-587, :602);
+// c1 is optional and may cover only the centre P1 x P1 tokens of the P x P grid (pad1 = (P - P1)/2), contributing 0
+// elsewhere.  One warp per token, 3 channels per lane.
+__global__ void pe_combine_kernel(const bf16* __restrict__ c0, const bf16* __restrict__ c1, int B, int P, int pad1,
+                                  SjNorm n0, SjNorm n1, SjNorm nf, bf16* __restrict__ y) {
+  const long long tok = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (tok >= (long long)B * P * P) return;
+  auto ln3 = [&](float (&v)[3], const SjNorm& nm) {
+    float mu = warp_sum(v[0] + v[1] + v[2]) / 96.f;
+    float d0 = v[0] - mu, d1 = v[1] - mu, d2 = v[2] - mu;
+    float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1 + d2 * d2) / 96.f + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] = (v[j] - mu) * rs * nm.g[lane + 32 * j] + nm.b[lane + 32 * j];
+  };
+  float a[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) a[j] = __bfloat162float(c0[tok * 96 + lane + 32 * j]);
+  ln3(a, n0);
+  if (c1) {
+    const int pj = (int)(tok % P) - pad1, pi = (int)((tok / P) % P) - pad1, P1 = P - 2 * pad1;
+    if (pi >= 0 && pj >= 0 && pi < P1 && pj < P1) {
+      const long long t1 = ((tok / ((long long)P * P)) * P1 + pi) * P1 + pj;
+      float m[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) m[j] = __bfloat162float(c1[t1 * 96 + lane + 32 * j]);
+      ln3(m, n1);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) a[j] += m[j];
+    }
+  }
+  ln3(a, nf);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) y[tok * 96 + lane + 32 * j] = __float2bfloat16_rn(a[j]);
+}
+
 // ---------------------------------------------------------------- FG-MSA offset network
 // one block (384 threads = output channels) per (b, image row i, 8-pixel half row): the grouped 3x3 conv
 // weights are read once per block and reused for the 8 pixels
@@ -513,6 +580,20 @@ void patch_embed(Ctx& c, const PatchEmbedP& p) {
   int grid = cdiv(ntok, PE_TOK);
   if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "patch_embed", patch_embed_kernel<bf16>, grid, p.E, 0, p);
   else SJ_LAUNCH(c, "patch_embed", patch_embed_kernel<float>, grid, p.E, 0, p);
+}
+
+void im2col4(Ctx& c, const void* img, int itype, int B, int S, int Cin, int es, int Kpad, void* A) {
+  if (!c.ok() || c.dry) return;
+  if (Kpad % 8 || Kpad < 16 * Cin) { c.fail(SJ_EINVAL); return; }
+  const long long n = (long long)B * (S / 4) * (S / 4) * (Kpad / 8);
+  SJ_LAUNCH(c, "im2col4", im2col4_kernel, cdiv(n, 256), 256, 0, img, itype, B, S, Cin, es, Kpad, (bf16*)A);
+}
+void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, const SjNorm& n0, const SjNorm& n1,
+                const SjNorm& nf, void* y) {
+  if (!c.ok() || c.dry) return;
+  const long long ntok = (long long)B * P * P;
+  SJ_LAUNCH(c, "pe_combine", pe_combine_kernel, cdiv(ntok, 8), 256, 0, (const bf16*)c0, (const bf16*)c1, B, P, pad1, n0, n1,
+            nf, (bf16*)y);
 }
 
 void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {

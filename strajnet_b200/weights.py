@@ -323,7 +323,10 @@ class Packer:
     def patch_embed(self, p: str) -> L.SjPatchEmbedW:
         s = L.SjPatchEmbedW()
         k = self.get(p + "proj.kernel")  # [4,4,Cin,E] -> [16*Cin, E]
-        s.proj = self.linear(k.reshape(-1, k.shape[-1]), self.get(p + "proj.bias"))
+        k2 = k.reshape(-1, k.shape[-1])
+        kpad = (k2.shape[0] + 63) // 64 * 64  # tensor-core copy: [E, Kpad], K zero-padded to a multiple of 64
+        tck = torch.cat([k2, k2.new_zeros(kpad - k2.shape[0], k2.shape[1])], 0).t().contiguous()
+        s.proj = self.linear(k2, self.get(p + "proj.bias"), tc_kernel=tck)
         s.norm = self.norm(p + "norm.")
         return s
 
