@@ -1,5 +1,7 @@
 // Attention cores of the fp32 path: one query per thread, K/V of the (batch, head) staged in
 // shared memory and read as warp-wide broadcasts.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sj {
@@ -227,11 +229,20 @@ void dispatch_mha(Ctx& c, const MhaP& p) {
 
 }  // namespace
 
+// A/B switch for the warp-MMA attention cores of the bf16 path (attn_mma.cu)
+static bool attn_mma_disabled() {
+  static const bool off = getenv("SJ_DISABLE_ATTN_MMA") != nullptr;
+  return off;
+}
+
 void window_attn_core(Ctx& c, const void* qkv, void* out, const float* rpb_table, int n_windows_total, int C,
                       int heads, int mask_mode, int H, int W, int shift, const float* mask, int nW) {
   if (!c.ok() || c.dry) return;
   int D = C / heads;
   if (D * heads != C || (D != 16 && D != 32)) { c.fail(SJ_EUNSUPPORTED); return; }
+  if (c.dtype == SJ_BF16 && !attn_mma_disabled() &&
+      attn_mma_window(c, qkv, out, rpb_table, n_windows_total, C, heads, mask_mode, H, W, shift, mask, nW))
+    return;
   dim3 grid(n_windows_total, heads);
 #define SJ_WA(T, DD)                                                                                              \
   SJ_LAUNCH(c, "window_attn_core", (window_attn_kernel<T, DD>), grid, 64, 0, (const T*)qkv, (T*)out, rpb_table, C, \
@@ -244,6 +255,7 @@ void window_attn_core(Ctx& c, const void* qkv, void* out, const float* rpb_table
 void mha_core(Ctx& c, const MhaP& p) {
   if (!c.ok() || c.dry) return;
   if (p.heads * p.D > p.ldo || p.batch <= 0 || p.Nq <= 0 || p.Nk <= 0) { c.fail(SJ_EINVAL); return; }
+  if (c.dtype == SJ_BF16 && !attn_mma_disabled() && attn_mma_mha(c, p)) return;
   if (c.dtype == SJ_BF16) dispatch_mha<bf16>(c, p);
   else dispatch_mha<float>(c, p);
 }

@@ -120,6 +120,10 @@ struct MhaP {
   const float* fg_table = nullptr;
 };
 void mha_core(Ctx& c, const MhaP& p);
+// bf16 warp-MMA variants (attn_mma.cu); return false when the shape is not covered
+bool attn_mma_mha(Ctx& c, const MhaP& p);
+bool attn_mma_window(Ctx& c, const void* qkv, void* out, const float* rpb_table, int n_windows_total, int C, int heads,
+                     int mask_mode, int H, int W, int shift, const float* mask, int nW);
 
 // ---- everything else (misc.cu) ----------------------------------------------------------------
 void relative_position_index(Ctx& c, int ws, int64_t* out);

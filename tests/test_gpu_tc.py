@@ -91,6 +91,40 @@ def test_patch_merging_bf16(sj, C, H):
     assert max_abs(y, O.patch_merging(x, w, p, H, H)) < 4e-2
 
 
+@pytest.mark.parametrize("C,heads,masked", [(32, 2, False), (32, 1, True), (192, 6, True), (384, 12, False)])
+def test_window_attention_bf16(sj, C, heads, masked):
+    """Warp-MMA window attention core (attn_mma.cu): head dims 16 and 32, explicit [nW,64,64] mask."""
+    w = O.make_block_weights(C, heads, seed=7)
+    layer = sj.WindowAttention(C, (8, 8), heads, dtype="bfloat16")
+    layer.set_weights(sub(w, "attn."))
+    nW = 4
+    x = _bf(randn((2 * nW, 64, C), 8))
+    mask = torch.from_numpy(O.shift_attn_mask(16, 16, 8, 4)).float() if masked else None
+    ref = O.window_attention(x, w, "attn.", heads, 8, mask)
+    err = max_abs(layer(x, mask=mask), ref)
+    print(f"window attention bf16 C={C} heads={heads}: max abs err {err:.3e}")
+    assert err < 3e-2
+
+
+@pytest.mark.parametrize("mode", ["normal", "no_occ", "all_padded"])
+def test_traj_cross_attention_bf16_masks(sj, mode):
+    """tfa mask semantics on the warp-MMA cores: partially and fully masked rows (uniform attention, Q7)."""
+    from tests.test_gpu_parity import _traj_inputs
+    w = oracle_model()
+    layer = sj.TrajNetCrossAttention(dict(traj_heads=4, att_heads=6, out_dim=384, no_attn=False), pic_size=(16, 16),
+                                     pic_dim=384, dtype="bfloat16")
+    layer.set_weights(sub(w, "trajnet_attn."))
+    pic = _bf(randn((2, 8, 16, 16, 384), 17))
+    obs, occ = _traj_inputs(2, 3, mode)
+    out = layer(pic, obs, occ, None, training=False)
+    ref = O.trajnet_cross_attention(pic, obs, occ, w)
+    err = max_abs(out, ref)
+    rmax = ref.abs().max().item()
+    print(f"traj cross attention bf16 ({mode}): max abs err {err:.3e}, max |ref| {rmax:.2f}")
+    # bf16 chain through three LayerNorms (eps 1e-3): gated relative to the output range, like the whole model
+    assert torch.isfinite(out).all() and err < 0.05 * rmax
+
+
 def test_traj_cross_attention_bf16(sj):
     w = oracle_model()
     layer = sj.TrajNetCrossAttention(dict(traj_heads=4, att_heads=6, out_dim=384, no_attn=False), pic_size=(16, 16),
