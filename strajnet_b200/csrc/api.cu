@@ -58,16 +58,22 @@ void linear(Ctx& c, const void* A, int lda, const SjLinear& w, void* C, int ldc,
 }
 
 // ---- SwinTransformerBlock.call (modules.py:220-262) ---------------------------------------------
-void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int B, int H, int W, int C, int heads,
-                     int ws, int shift, const int* map) {
-  if (ws != 8 || H % 8 || W % 8 || H < 8 || W < 8 || C % 16 || heads <= 0 || C % heads) { c.fail(SJ_EUNSUPPORTED); return; }
+// in_mean/in_rstd: norm1 statistics of x when the producer of x already emitted them; out_mean/out_rstd: where to put
+// the eps-1e-5 LayerNorm statistics of y for the next block.  Returns true when the out statistics were written
+// (tensor-core path only: they come out of the fc2 epilogue).
+bool swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int B, int H, int W, int C, int heads,
+                     int ws, int shift, const int* map, const float* in_mean = nullptr, const float* in_rstd = nullptr,
+                     float* out_mean = nullptr, float* out_rstd = nullptr) {
+  if (ws != 8 || H % 8 || W % 8 || H < 8 || W < 8 || C % 16 || heads <= 0 || C % heads) { c.fail(SJ_EUNSUPPORTED); return false; }
   if (H <= ws || W <= ws) shift = 0;  // modules.py:173-175
-  if (shift < 0 || shift >= ws) { c.fail(SJ_EINVAL); return; }
+  if (shift < 0 || shift >= ws) { c.fail(SJ_EINVAL); return false; }
   const int L = H * W;
   const long long M = (long long)B * L;
   size_t mark = c.ws.mark();
   float* mean = (float*)c.alloc(M * 4);
   float* rstd = (float*)c.alloc(M * 4);
+  float* mean2 = (float*)c.alloc(M * 4);
+  float* rstd2 = (float*)c.alloc(M * 4);
   if (!map) {
     int* m = (int*)c.alloc((size_t)L * 4);
     window_token_map(c, H, W, ws, shift, m);
@@ -79,11 +85,20 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   void* hbuf = c.alloc_act(M * 4 * C);
 
   static const bool fused_off = getenv("SJ_DISABLE_FUSED_WMSA") != nullptr;
+  static const bool stats_off = getenv("SJ_DISABLE_FUSED_STATS") != nullptr;
+  const bool tc = c.dtype == SJ_BF16 && w.proj.w_tc && w.fc2.w_tc;
   const bool fused = c.dtype == SJ_BF16 && !fused_off && w.qkv_ln.w_tc && tc_wmsa_supported(B, H, W, C, heads, ws, shift);
+  // norm2 / next-block norm1 statistics straight out of the producing epilogue (one n-tile must cover the row)
+  const bool stats_fused = tc && !stats_off && tc_gemm_stats_ok(C);
+  bool have_stats2 = false;
   if (fused) {
     // K1: the whole attention half as one tcgen05 kernel (tc_wmsa.cu)
-    ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
-    tc_wmsa(c, x, x1, mean, rstd, w, B, H, W, shift);
+    if (!in_mean) {
+      ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
+      in_mean = mean; in_rstd = rstd;
+    }
+    tc_wmsa(c, x, x1, in_mean, in_rstd, w, B, H, W, shift, mean2, rstd2);
+    have_stats2 = true;
   } else if (c.dtype == SJ_BF16) {
     // tensor-core path: norm1 + roll + partition as one gather pass, then a plain GEMM
     layernorm_gather(c, x, x1, (int)M, C, w.norm1.g, w.norm1.b, 1e-5f, map, L);
@@ -104,18 +119,27 @@ void swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
     g.M = (int)M; g.N = C; g.K = C;
     g.cm.map = map; g.cm.map_len = L;
     g.R = x; g.ldr = C;
+    if (stats_fused) { g.st_mean = mean2; g.st_rstd = rstd2; g.st_eps = 1e-5f; have_stats2 = true; }
     gemm(c, g);
   }
-  ln_stats(c, x1, (int)M, C, C, 1e-5f, mean, rstd);
+  if (!have_stats2) ln_stats(c, x1, (int)M, C, C, 1e-5f, mean2, rstd2);
   {  // norm2 -> fc1 -> GELU   (modules.py:260, :41-42)
     GemmP g;
     g.A = x1; g.lda = C; g.set_weights(w.fc1); g.ldw = 4 * C; g.C = hbuf; g.ldc = 4 * C;
     g.M = (int)M; g.N = 4 * C; g.K = C; g.act = ACT_GELU;
-    g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
+    g.ln_mean = mean2; g.ln_rstd = rstd2; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
     gemm(c, g);
   }
-  linear(c, hbuf, 4 * C, w.fc2, y, C, (int)M, C, 4 * C, ACT_NONE, x1, C);  // fc2 + residual
+  bool wrote = false;
+  {  // fc2 + residual
+    GemmP g;
+    g.A = hbuf; g.lda = 4 * C; g.set_weights(w.fc2); g.ldw = C; g.C = y; g.ldc = C;
+    g.M = (int)M; g.N = C; g.K = 4 * C; g.R = x1; g.ldr = C;
+    if (out_mean && stats_fused) { g.st_mean = out_mean; g.st_rstd = out_rstd; g.st_eps = 1e-5f; wrote = true; }
+    gemm(c, g);
+  }
   c.ws.release(mark);
+  return wrote;
 }
 
 // ---- PatchMerging.call (modules.py:274-292) -----------------------------------------------------
@@ -145,14 +169,22 @@ void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBa
   size_t mark = c.ws.mark();
   void* tmp = w.depth > 1 ? c.alloc_act(n) : nullptr;
   int* maps[2] = {(int*)c.alloc((size_t)H * W * 4), (int*)c.alloc((size_t)H * W * 4)};
+  // norm1 statistics handed from block i (fc2 epilogue) to block i+1
+  float* st[2][2];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) st[i][j] = (float*)c.alloc((size_t)B * H * W * 4);
   const int sh = (H <= ws || W <= ws) ? 0 : ws / 2;
   window_token_map(c, H, W, ws, 0, maps[0]);
   window_token_map(c, H, W, ws, sh, maps[1]);
   const void* cur = x;
+  bool have = false;
   for (int i = 0; i < w.depth; ++i) {
     void* dst = ((w.depth - 1 - i) % 2 == 0) ? res : tmp;
     int shift = (i % 2 == 0) ? 0 : sh;  // modules.py:331-332
-    swin_block_impl(c, cur, dst, w.blocks_host[i], B, H, W, C, w.heads, ws, shift, maps[i % 2]);
+    const bool want = i + 1 < w.depth;
+    have = swin_block_impl(c, cur, dst, w.blocks_host[i], B, H, W, C, w.heads, ws, shift, maps[i % 2],
+                           have ? st[(i + 1) % 2][0] : nullptr, have ? st[(i + 1) % 2][1] : nullptr,
+                           want ? st[i % 2][0] : nullptr, want ? st[i % 2][1] : nullptr);
     cur = dst;
   }
   if (w.has_down) {

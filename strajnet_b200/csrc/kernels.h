@@ -37,6 +37,10 @@ struct GemmP {
   const float* ln_b = nullptr;
   int ln_gstride = 0;
   int act = ACT_NONE;
+  // optional (tensor-core path, N <= 256 in one tile): LayerNorm statistics of the output rows, written at the C row
+  float* st_mean = nullptr;
+  float* st_rstd = nullptr;
+  float st_eps = 0.f;
   // A_CONV3: output H x Wd, input (H>>up) x (Wd>>up) x Cin, M = images*H*Wd, K = 9*Cin
   // A_MERGE: input H x Wd x Cin, M = B*(H/2)*(Wd/2), K = 4*Cin
   int H = 0, Wd = 0, Cin = 0, up = 0;
@@ -72,9 +76,14 @@ struct TcGemmP {
   const float* ln_rstd = nullptr;
   const float* ln_s = nullptr;  // column sums of the folded weights, [G][N]
   int ln_gstride = 0;
+  float* st_mean = nullptr;  // LayerNorm statistics of the output rows (needs pick_bn(N) == N)
+  float* st_rstd = nullptr;
+  float st_eps = 0.f;
   int dbg_shift = 0, dbg_bo = 0;  // hardware-semantics probe (sj_debug_gemm_shift)
 };
 bool tc_gemm_supported(const TcGemmP& p);
+// true when tc_gemm can emit output-row statistics for an N-wide output (one n-tile)
+bool tc_gemm_stats_ok(int N);
 void tc_gemm(Ctx& c, const TcGemmP& p);
 int num_sms();
 
@@ -181,8 +190,9 @@ void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
 // ---- K1: fused window-MSA on tcgen05 (tc_wmsa.cu), bf16, C = 96 / 3 heads / window 8 ----------------
 bool tc_wmsa_supported(int B, int H, int W, int C, int heads, int ws, int shift);
 // out[token] = x[token] + proj(window_attention(norm1(x)))  for x, out bf16 [B, H*W, 96]; mean/rstd = norm1 stats of x
+// mean2/rstd2 (optional): LayerNorm statistics (eps 1e-5) of the output rows, for norm2
 void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
-             int H, int W, int shift);
+             int H, int W, int shift, float* mean2, float* rstd2);
 
 // tcgen05 decoder head (tc_outconv.cu): bf16 inputs [B*8,256,256,48], fp32 logits out
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,

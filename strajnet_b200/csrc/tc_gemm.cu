@@ -41,6 +41,9 @@ struct KParams {
   const float* ln_rstd;
   const float* ln_s;
   int ln_gstride;
+  float* st_mean;  // optional: LayerNorm statistics of the OUTPUT rows (needs BN == N), written at the C row index
+  float* st_rstd;
+  float st_eps;
   int a_rows;     // rows per A stage (128; 256 for the shifted-view probe)
   int dbg_shift;  // probe: the MMA reads A rows [shift, shift+128) of the stage
   int dbg_bo;     // probe: set the descriptor base_offset field from the start address
@@ -62,6 +65,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float2* stat_s = reinterpret_cast<float2*>(bars + 32);  // [2 accumulator stages][128 rows] partial (sum, sum of squares)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -176,6 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.BN;
+      float st_s = 0.f, st_q = 0.f;  // statistics of this thread's share of the (bf16-rounded) output row
       // residual rows are fetched BEFORE the TMEM load of the same columns so the global-memory latency overlaps
       // the tcgen05.ld round trip; everything is fully unrolled so v[] / rr[] stay in registers
       auto chunk = [&](auto cnt_tag, int c) {
@@ -212,12 +217,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               v[i + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
             }
           }
+          if (p.st_mean) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float r = __bfloat162float(__float2bfloat16_rn(v[i + j]));
+              st_s += r;
+              st_q = fmaf(r, r, st_q);
+            }
+          }
           st8_bf16(p.C + crow * p.ldc + n + i, v + i);
         }
       };
       int c = c_begin;
       for (; c + 32 <= c_end; c += 32) chunk(std::integral_constant<int, 32>{}, c);
       if (c < c_end) chunk(std::integral_constant<int, 16>{}, c);
+      if (p.st_mean) {
+        // the two warps of a TMEM lane quarter each hold half of the row: combine through shared memory
+        const int rloc = quarter * 32 + lane;
+        if (half) stat_s[as * BM + rloc] = make_float2(st_s, st_q);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (!half && valid) {
+          const float2 o2 = stat_s[as * BM + rloc];
+          const float mu = (st_s + o2.x) / (float)p.N;
+          const float var = fmaxf((st_q + o2.y) / (float)p.N - mu * mu, 0.f);
+          p.st_mean[crow] = mu;
+          p.st_rstd[crow] = rsqrtf(var + p.st_eps);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -277,6 +303,8 @@ int num_sms() {
   return g_num_sms;
 }
 
+bool tc_gemm_stats_ok(int N) { return N % 16 == 0 && pick_bn(N) == N; }
+
 bool tc_gemm_supported(const TcGemmP& a) {
   if (!a.Bw || a.K < 64 || a.K % 32 || a.N % 16 || pick_bn(a.N) == 0) return false;
   if (a.a_mode == 0 && (a.lda % 8)) return false;
@@ -302,6 +330,10 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   p.bias = a.bias; p.bias_gstride = a.bias_gstride; p.act = a.act;
   p.R = (const bf16*)a.R; p.ldr = a.ldr; p.C = (bf16*)a.C; p.ldc = a.ldc; p.cm = a.cm;
   p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_s = a.ln_s; p.ln_gstride = a.ln_gstride;
+  if (a.st_mean) {
+    if (p.n_tiles != 1 || !a.st_rstd) { c.fail(SJ_EUNSUPPORTED); return; }
+    p.st_mean = a.st_mean; p.st_rstd = a.st_rstd; p.st_eps = a.st_eps;
+  }
   p.a_rows = a.dbg_shift > 0 ? 256 : BM; p.dbg_shift = a.dbg_shift; p.dbg_bo = a.dbg_bo;
 
   CUtensorMap mapA, mapB;
@@ -339,7 +371,7 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256;
+  const size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * BM * sizeof(float2);
   const int tiles = p.m_tiles * p.n_tiles * p.groups;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
@@ -383,6 +415,7 @@ void gemm(Ctx& c, const GemmP& g) {
       t.Bw = g.W_tc; t.M = g.M; t.N = g.N; t.K = g.K; t.groups = g.groups;
       t.bias = ln ? g.tc_bias : g.bias; t.bias_gstride = g.bias_gstride; t.act = g.act;
       t.R = g.R; t.ldr = g.ldr; t.C = g.C; t.ldc = g.ldc; t.cm = g.cm;
+      t.st_mean = g.st_mean; t.st_rstd = g.st_rstd; t.st_eps = g.st_eps;
       if (ln) {
         t.ln_mean = g.ln_mean; t.ln_rstd = g.ln_rstd; t.ln_s = g.tc_colsum;
         t.ln_gstride = g.groups > 1 ? g.N : 0;
@@ -394,6 +427,7 @@ void gemm(Ctx& c, const GemmP& g) {
       }
     }
   }
+  if (g.st_mean) { c.fail(SJ_EUNSUPPORTED); return; }  // fused output statistics exist on the tensor-core path only
   gemm_simt(c, g);
 }
 

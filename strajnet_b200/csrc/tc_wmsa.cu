@@ -63,6 +63,8 @@ struct WmsaP {
   const float* biasf;
   const float* table;  // [225, NH]
   const float* bproj;  // [C]
+  float* mean2;        // optional: norm2 statistics of the output rows
+  float* rstd2;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -303,6 +305,7 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       tc_fence_after();
       const bf16* xin = p.x + tok * C;
       bf16* dst = p.out + tok * C;
+      float st_s = 0.f, st_q = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
@@ -312,9 +315,19 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           float xr[8];
           ld8_bf16(xin + c0 + i, xr);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i + j] += p.bproj[c0 + i + j] + xr[j];
+          for (int j = 0; j < 8; ++j) {
+            v[i + j] += p.bproj[c0 + i + j] + xr[j];
+            const float rr = __bfloat162float(__float2bfloat16_rn(v[i + j]));  // statistics of the stored values
+            st_s += rr;
+            st_q = fmaf(rr, rr, st_q);
+          }
           st8_bf16(dst + c0 + i, v + i);
         }
+      }
+      if (p.mean2) {
+        const float mu = st_s * (1.0f / C);
+        p.mean2[tok] = mu;
+        p.rstd2[tok] = rsqrtf(fmaxf(st_q * (1.0f / C) - mu * mu, 0.f) + 1e-5f);
       }
       tc_fence_before();
       __syncwarp();
@@ -339,7 +352,7 @@ bool tc_wmsa_supported(int B, int H, int W, int Cc, int heads, int ws, int shift
 
 // x, out: bf16 [B, H*W, 96]; mean/rstd: fp32 [B*H*W] (norm1 statistics of x); w: norm1-folded qkv (tensor-core copy)
 void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
-             int H, int W, int shift) {
+             int H, int W, int shift, float* mean2, float* rstd2) {
   if (!c.ok() || c.dry) return;
   if (!w.qkv_ln.w_tc || !w.qkv_ln.tc_colsum || !w.qkv_ln.tc_bias || !w.proj.w_tc || !w.proj.b || !w.rpb_table) {
     c.fail(SJ_EINVAL);
@@ -365,6 +378,7 @@ void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* r
   p.wpr = W / 8; p.nW = (H / 8) * (W / 8);
   p.num_tiles = B * p.nW / 2;
   p.x = (const bf16*)x; p.out = (bf16*)out; p.mean = mean; p.rstd = rstd;
+  p.mean2 = mean2; p.rstd2 = rstd2;
   p.colsum = w.qkv_ln.tc_colsum; p.biasf = w.qkv_ln.tc_bias; p.table = w.rpb_table; p.bproj = w.proj.b;
   const size_t smem = 1024 + SMEM_BYTES;
   if (cudaFuncSetAttribute(tc_wmsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
