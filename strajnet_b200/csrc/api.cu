@@ -411,6 +411,11 @@ void traj_impl(Ctx& c, const void* pic, const float* obs, const float* occ, void
 
 // ---- Pyramid3DDecoder.call (modules.py:739-772) --------------------------------------------------
 void upconv(Ctx& c, const void* x, void* y, const SjLinear& w, int NB, int Hin, int Cin, int Cout) {
+  static const bool up4_off = getenv("SJ_DISABLE_UPCONV4") != nullptr;
+  if (c.dtype == SJ_BF16 && w.w_tc && w.b && !up4_off && tc_upconv4_supported(Hin, Hin, Cin, Cout)) {
+    tc_upconv4(c, x, y, w.w_tc, w.b, NB, Hin, Hin);
+    return;
+  }
   if (c.dtype == SJ_BF16 && w.w_tc && w.b && tc_upconv_supported(Hin, Hin, Cin, Cout)) {
     tc_upconv(c, x, y, w.w_tc, w.b, NB, Hin, Hin, Cin, Cout);
     return;

@@ -94,6 +94,10 @@ bool tc_upconv_supported(int H, int W, int Cin, int Cout);
 void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bias, int NB, int H, int W, int Cin,
                int Cout);
 
+// small-channel variant (tc_upconv4.cu): Cin = 96, Cout = 48, all four sub-pixel phases per CTA with stacked-N MMAs
+bool tc_upconv4_supported(int H, int W, int Cin, int Cout);
+void tc_upconv4(Ctx& c, const void* x, void* y, const void* w_tc, const float* bias, int NB, int H, int W);
+
 // ---- LayerNorm family (norm.cu) ---------------------------------------------------------------
 // per-row mean / rstd (biased variance) of x[rows, C] (row stride ld)
 void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* mean, float* rstd);
