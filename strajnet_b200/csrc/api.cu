@@ -416,6 +416,11 @@ void upconv(Ctx& c, const void* x, void* y, const SjLinear& w, int NB, int Hin, 
     tc_upconv4(c, x, y, w.w_tc, w.b, NB, Hin, Hin);
     return;
   }
+  static const bool up1p_off = getenv("SJ_DISABLE_UPCONV1P") != nullptr;
+  if (c.dtype == SJ_BF16 && w.w_tc && w.b && !up1p_off && tc_upconv1p_supported(Hin, Hin, Cin, Cout)) {
+    tc_upconv1p(c, x, y, w.w_tc, w.b, NB, Hin, Hin);
+    return;
+  }
   if (c.dtype == SJ_BF16 && w.w_tc && w.b && tc_upconv_supported(Hin, Hin, Cin, Cout)) {
     tc_upconv(c, x, y, w.w_tc, w.b, NB, Hin, Hin, Cin, Cout);
     return;

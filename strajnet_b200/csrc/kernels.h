@@ -98,6 +98,10 @@ void tc_upconv(Ctx& c, const void* x, void* y, const void* w_tc, const float* bi
 bool tc_upconv4_supported(int H, int W, int Cin, int Cout);
 void tc_upconv4(Ctx& c, const void* x, void* y, const void* w_tc, const float* bias, int NB, int H, int W);
 
+// mid-channel variant (tc_upconv1p.cu): Cin = 128, Cout = 96, one sub-pixel phase per CTA with resident weights
+bool tc_upconv1p_supported(int H, int W, int Cin, int Cout);
+void tc_upconv1p(Ctx& c, const void* x, void* y, const void* w_tc, const float* bias, int NB, int H, int W);
+
 // ---- LayerNorm family (norm.cu) ---------------------------------------------------------------
 // per-row mean / rstd (biased variance) of x[rows, C] (row stride ld)
 void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* mean, float* rstd);
