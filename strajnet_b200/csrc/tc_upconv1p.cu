@@ -54,7 +54,7 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
   float* bias_s = reinterpret_cast<float*>(bars + 32);  // [COUT]
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   for (int i = threadIdx.x; i < COUT; i += NTHREADS) bias_s[i] = p.bias[i];
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
@@ -99,21 +99,21 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t A_HI = desc_hi(KC * 2, PW * KC * 2), B_HI = desc_hi(KC * 2, 8 * KC * 2);
-      const uint32_t idesc = make_idesc_bf16(128, COUT);
-      const uint32_t b_lo = desc_lo(smem_u32(smem_b));
-      int as_ = 0, acc = 0;
-      uint32_t aph = 0, tph = 0;
-      mbar_wait(bfull, 0);
+    // the whole warp runs the loop (uniform control flow, operands in uniform registers); one elected lane issues
+    constexpr uint32_t A_HI = desc_hi(KC * 2, PW * KC * 2), B_HI = desc_hi(KC * 2, 8 * KC * 2);
+    const uint32_t idesc = make_idesc_bf16(128, COUT);
+    const uint32_t b_lo = desc_lo(smem_u32(smem_b));
+    int as_ = 0, acc = 0;
+    uint32_t aph = 0, tph = 0;
+    mbar_wait(bfull, 0);
+    tc_fence_after();
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
+      mbar_wait(&tempty[acc], tph ^ 1);
+      mbar_wait(&afull[as_], aph);
       tc_fence_after();
-      for (int t = t_first; t < p.num_tiles; t += t_step) {
-        mbar_wait(&tempty[acc], tph ^ 1);
-        tc_fence_after();
-        mbar_wait(&afull[as_], aph);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        const uint32_t a_lo = desc_lo(smem_u32(smem + as_ * A_SLOT));
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      const uint32_t a_lo = desc_lo(smem_u32(smem + as_ * A_SLOT));
+      if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
 #pragma unroll
@@ -128,14 +128,18 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         umma_commit(&aempty[as_]);
         umma_commit(&tfull[acc]);
-        if (++as_ == NA) { as_ = 0; aph ^= 1; }
-        if (++acc == NACC) { acc = 0; tph ^= 1; }
       }
+      __syncwarp();
+      if (++as_ == NA) { as_ = 0; aph ^= 1; }
+      if (++acc == NACC) { acc = 0; tph ^= 1; }
     }
   } else {
     const int quarter = warp % 4, half = (warp - 2) / 4;  // two warps per lane quarter, 48 columns each
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
     const int c0 = half * (COUT / 2);
+    float bias_r[COUT / 2];  // this thread's 48 output channels never change: bias lives in registers
+#pragma unroll
+    for (int i = 0; i < COUT / 2; ++i) bias_r[i] = bias_s[c0 + i];
     int acc = 0;
     uint32_t tph = 0;
     for (int t = t_first; t < p.num_tiles; t += t_step) {
@@ -149,11 +153,7 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         float v[32];
         tmem_ld32(t_addr, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-          v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
-          v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i] + bias_r[i], ACT_ELU);
 #pragma unroll
         for (int i = 0; i < 32; i += 8) st8_bf16(dst + i, v + i);
       }
@@ -161,11 +161,7 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         float v[16];
         tmem_ld16(t_addr + 32, v);
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 32 + i);
-          v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
-          v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
-        }
+        for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i] + bias_r[32 + i], ACT_ELU);
 #pragma unroll
         for (int i = 0; i < 16; i += 8) st8_bf16(dst + 32 + i, v + i);
       }

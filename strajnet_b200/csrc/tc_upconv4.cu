@@ -67,7 +67,7 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* bias_s = reinterpret_cast<float*>(bars + 16);  // [COUT]
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   for (int i = threadIdx.x; i < COUT; i += NTHREADS) bias_s[i] = p.bias[i];
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
@@ -118,26 +118,26 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // one entry per MMA of a 16-channel step: view, first weight slot, first ring phase, stacked phases
-      struct Op { int ro, dx, slot, ring, cnt; };
-      constexpr Op OPS[10] = {{1, 1, 0, 0, 4}, {0, 1, 4, 0, 2}, {1, 2, 6, 1, 2}, {2, 1, 8, 2, 2}, {1, 0, 10, 0, 1},
-                              {1, 0, 11, 3, 1}, {0, 0, 12, 0, 1}, {0, 2, 13, 1, 1}, {2, 2, 14, 2, 1}, {2, 0, 15, 3, 1}};
-      constexpr uint32_t A_HI = desc_hi(KC * 2, PW * KC * 2), B_HI = desc_hi(KC * 2, 8 * KC * 2);
-      const uint32_t idesc1 = make_idesc_bf16(128, COUT), idesc2 = make_idesc_bf16(128, 2 * COUT),
-                     idesc4 = make_idesc_bf16(128, 4 * COUT);
-      const uint32_t b_lo = desc_lo(smem_u32(smem_b));
-      int as_ = 0, acc = 0;
-      uint32_t aph = 0, tph = 0;
-      mbar_wait(bfull, 0);
+    // the whole warp runs the loop (uniform control flow, operands in uniform registers); one elected lane issues
+    // one entry per MMA of a 16-channel step: view, first weight slot, first ring phase, stacked phases
+    struct Op { int ro, dx, slot, ring, cnt; };
+    constexpr Op OPS[10] = {{1, 1, 0, 0, 4}, {0, 1, 4, 0, 2}, {1, 2, 6, 1, 2}, {2, 1, 8, 2, 2}, {1, 0, 10, 0, 1},
+                            {1, 0, 11, 3, 1}, {0, 0, 12, 0, 1}, {0, 2, 13, 1, 1}, {2, 2, 14, 2, 1}, {2, 0, 15, 3, 1}};
+    constexpr uint32_t A_HI = desc_hi(KC * 2, PW * KC * 2), B_HI = desc_hi(KC * 2, 8 * KC * 2);
+    const uint32_t idesc1 = make_idesc_bf16(128, COUT), idesc2 = make_idesc_bf16(128, 2 * COUT),
+                   idesc4 = make_idesc_bf16(128, 4 * COUT);
+    const uint32_t b_lo = desc_lo(smem_u32(smem_b));
+    int as_ = 0, acc = 0;
+    uint32_t aph = 0, tph = 0;
+    mbar_wait(bfull, 0);
+    tc_fence_after();
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[acc], tph ^ 1);
+      mbar_wait(&afull[as_], aph);
       tc_fence_after();
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        mbar_wait(&tempty[acc], tph ^ 1);
-        tc_fence_after();
-        mbar_wait(&afull[as_], aph);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        const uint32_t a_lo = desc_lo(smem_u32(smem + as_ * A_SLOT));
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      const uint32_t a_lo = desc_lo(smem_u32(smem + as_ * A_SLOT));
+      if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
 #pragma unroll
@@ -154,15 +154,19 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         umma_commit(&aempty[as_]);
         umma_commit(&tfull[acc]);
-        if (++as_ == NA) { as_ = 0; aph ^= 1; }
-        if (++acc == 2) { acc = 0; tph ^= 1; }
       }
+      __syncwarp();
+      if (++as_ == NA) { as_ = 0; aph ^= 1; }
+      if (++acc == 2) { acc = 0; tph ^= 1; }
     }
   } else {
     const int quarter = warp % 4, py = (warp - 2) / 4;
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
     // ring order p00 | p01 | p11 | p10: row phase 0 reads columns [0, 96) as (px0, px1), row phase 1 reads
     // [96, 192) as (px1, px0)
+    float bias_r[COUT];  // bias lives in registers (both phases of this thread use the same 48 channels)
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) bias_r[i] = bias_s[i];
     int acc = 0;
     uint32_t tph = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -180,11 +184,7 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           float v[32];
           tmem_ld32(t_addr + half * COUT, v);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + i);
-            v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
-            v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
-          }
+          for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i] + bias_r[i], ACT_ELU);
 #pragma unroll
           for (int i = 0; i < 32; i += 8) st8_bf16(dst + i, v + i);
         }
@@ -192,11 +192,7 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           float v[16];
           tmem_ld16(t_addr + half * COUT + 32, v);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 32 + i);
-            v[i] = act_fast(v[i] + b4.x, ACT_ELU); v[i + 1] = act_fast(v[i + 1] + b4.y, ACT_ELU);
-            v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
-          }
+          for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i] + bias_r[32 + i], ACT_ELU);
 #pragma unroll
           for (int i = 0; i < 16; i += 8) st8_bf16(dst + 32 + i, v + i);
         }
