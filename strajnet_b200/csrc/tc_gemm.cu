@@ -67,7 +67,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float2* stat_s = reinterpret_cast<float2*>(bars + 32);  // [2 accumulator stages][128 rows] partial (sum, sum of squares)
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
@@ -123,30 +123,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.BN);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // the whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane
+    // issues the MMAs and commits
+    const uint32_t idesc = make_idesc_bf16(BM, p.BN);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * p.BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES) + p.dbg_shift * 128;
-          uint64_t da = make_smem_desc(a_addr, 128);
-          if (p.dbg_bo) da |= (uint64_t)((a_addr >> 7) & 7) << 49;  // matrix base offset, bits [49,52)
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes), 128);
+        const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES) + p.dbg_shift * 128;
+        uint64_t da = make_smem_desc(a_addr, 128);
+        if (p.dbg_bo) da |= (uint64_t)((a_addr >> 7) & 7) << 49;  // matrix base offset, bits [49,52)
+        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * b_stage_bytes), 128);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K=16 step inside the 128B swizzle row
             umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb == p.k_blocks - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     const int quarter = warp % 4, half = (warp - 2) / 4;  // two warps per TMEM lane quarter, each takes half the columns
