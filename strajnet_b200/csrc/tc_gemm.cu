@@ -41,6 +41,7 @@ struct KParams {
   const float* ln_rstd;
   const float* ln_s;
   int ln_gstride;
+  int vec_smem;    // bias / column-sum vectors of all groups staged in shared memory (floats per vector, 0 = read from global)
   float* st_mean;  // optional: LayerNorm statistics of the OUTPUT rows (needs BN == N), written at the C row index
   float* st_rstd;
   float st_eps;
@@ -66,6 +67,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float2* stat_s = reinterpret_cast<float2*>(bars + 32);  // [2 accumulator stages][128 rows] partial (sum, sum of squares)
+  float* vec_s = reinterpret_cast<float*>(stat_s + 2 * BM);  // [bias: vec_smem floats][column sums: vec_smem floats]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -155,6 +157,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int quarter = warp % 4, half = (warp - 2) / 4;  // two warps per TMEM lane quarter, each takes half the columns
     const int csplit = ((p.BN / 16 + 1) / 2) * 16;
     const int c_begin = half ? csplit : 0, c_end = half ? p.BN : csplit;
+    if (p.vec_smem) {
+      // per-column epilogue vectors: staged once, then read as shared-memory broadcasts (global loads of them miss L1
+      // behind the streaming residual / output traffic and show up as long-scoreboard stalls)
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < p.vec_smem; i += NTHREADS - 64) {
+        vec_s[i] = p.bias ? p.bias[i] : 0.f;
+        if (LN) vec_s[p.vec_smem + i] = p.ln_s[i];
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -178,8 +190,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           rstd = p.ln_rstd[arow];
         }
       }
-      const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
-      const float* lns = LN ? p.ln_s + (long long)g * p.ln_gstride : nullptr;
+      const float* bias = p.bias ? (p.vec_smem ? vec_s : p.bias) + (long long)g * p.bias_gstride : nullptr;
+      const float* lns = LN ? (p.vec_smem ? vec_s + p.vec_smem : p.ln_s) + (long long)g * p.ln_gstride : nullptr;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.BN;
@@ -374,7 +386,17 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * BM * sizeof(float2);
+  size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * BM * sizeof(float2);
+  {
+    // stage the per-column vectors when they are dense ([groups][N]) and fit beside the operand ring
+    const int vec = p.groups * a.N;
+    const bool dense = (p.groups == 1 || ((!a.bias || a.bias_gstride == a.N) && (!a.ln_mean || a.ln_gstride == a.N)));
+    const size_t need = (size_t)vec * 4 * (a.ln_mean ? 2 : 1);
+    if ((a.bias || a.ln_mean) && dense && smem + need <= 225 * 1024 && need <= 24 * 1024) {
+      p.vec_smem = vec;
+      smem += need;
+    }
+  }
   const int tiles = p.m_tiles * p.n_tiles * p.groups;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
