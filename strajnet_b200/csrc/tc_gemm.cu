@@ -339,6 +339,15 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.groups = a.groups < 1 ? 1 : a.groups;
   p.BN = pick_bn(a.N);
   p.m_tiles = cdiv(a.M, BM);
+  if (!a.st_mean) {
+    // small problems are latency-bound: prefer the largest BN that still gives every SM a tile, else the narrowest
+    // (>= 32) so that the epilogue of each CTA is short
+    for (int bn = p.BN; bn >= 32; bn -= 16) {
+      if (a.N % bn) continue;
+      p.BN = bn;
+      if ((long long)p.m_tiles * (a.N / bn) * p.groups >= num_sms()) break;
+    }
+  }
   p.n_tiles = a.N / p.BN;
   p.k_blocks = a.a_mode == 2 ? 4 * cdiv(a.mC, BK) : cdiv(a.K, BK);
   p.a_mode = a.a_mode; p.a_inner = a.a_inner;
