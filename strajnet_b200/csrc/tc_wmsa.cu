@@ -17,7 +17,11 @@
 //     P (bf16) -> O_h = P . v_h (v_h is an MN-major B operand, no transpose) -> O_h/sum to smem ->
 //     proj accumulates O_h . Wproj[h] into a persistent TMEM accumulator.
 //   * TMEM: region A (128 columns) is reused for QKV_h -> S -> O_h, region B (96 columns) holds proj.
-//   * all weights (norm1-folded Wqkv 72 KB, Wproj 18 KB) stay resident in shared memory.
+//   * the weights of ONE head (norm1-folded Wqkv_h 18 KB, Wproj_h 6 KB) are streamed per head through two
+//     single-slot mbarrier-guarded buffers (freed right after the MMA that reads them, so the next head's weights
+//     arrive under the softmax); everything is staged in 32-channel SWIZZLE_64B chunks (K = 96 = 3 chunks, no
+//     padding).  110 KB of shared memory and 256 TMEM columns per CTA: TWO CTAs are resident per SM, so while one
+//     tile waits on an MMA / TMEM round trip the other tile's row threads run.
 // Warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = the 128 row threads.
 #include <cstdio>
 
@@ -30,28 +34,30 @@ namespace {
 using namespace tc;
 
 constexpr int C = 96, NH = 3, NTHREADS = 192;
-constexpr int X_CHUNK = 128 * 128;        // 16 KB: 128 rows x 64 channels
-constexpr int WQ_TILE = 96 * 128;         // 12 KB: (q|k|v of one head) x 64 channels
+constexpr int X_CHUNK = 128 * 64;         // 8 KB: 128 rows x 32 channels
+constexpr int WQ_CHUNK = 96 * 64;         // 6 KB: (q|k|v of one head) x 32 channels
 constexpr int WP_TILE = 96 * 64;          // 6 KB: proj rows x 32 channels of one head
 constexpr int QKV_TILE = 128 * 64;        // 8 KB: 128 rows x 32 dims
 constexpr int P_CHUNK = 128 * 128;        // 16 KB: 128 rows x 64 keys
 constexpr int OFF_X = 0;
-constexpr int OFF_WQ = OFF_X + 2 * X_CHUNK;
-constexpr int OFF_WP = OFF_WQ + NH * 2 * WQ_TILE;
-constexpr int OFF_Q = OFF_WP + NH * WP_TILE;
+constexpr int OFF_WQ = OFF_X + 3 * X_CHUNK;
+constexpr int OFF_WP = OFF_WQ + 3 * WQ_CHUNK;
+constexpr int OFF_Q = OFF_WP + WP_TILE;
 constexpr int OFF_K = OFF_Q + QKV_TILE;
 constexpr int OFF_V = OFF_K + QKV_TILE;
-constexpr int OFF_P = OFF_V + QKV_TILE;
-constexpr int OFF_AO = OFF_P + 2 * P_CHUNK;
-constexpr int OFF_TBL = OFF_AO + QKV_TILE;            // float [NH][228]
+constexpr int OFF_P = OFF_V + QKV_TILE;               // 72 KB: 1024-aligned for the 128-byte swizzle
+constexpr int OFF_AO = OFF_Q;                         // O_h aliases q_h (dead once S_h has been computed)
+constexpr int OFF_TBL = OFF_P + 2 * P_CHUNK;          // float [NH][228]
 constexpr int OFF_LN = OFF_TBL + NH * 228 * 4;        // float colsum[288], biasf[288]
 constexpr int OFF_RID = OFF_LN + 2 * 288 * 4;         // int [128]
 constexpr int OFF_BAR = (OFF_RID + 128 * 4 + 63) & ~63;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(OFF_P % 1024 == 0, "P tile alignment");
+static_assert(2 * (SMEM_BYTES + 1024 + 1024) <= 228 * 1024, "two CTAs per SM");
 constexpr float QSCALE = 0.17677669529663687f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { B_XFULL = 0, B_XEMPTY, B_WFULL, B_QKV, B_QKR, B_S, B_PR, B_O, B_AOR, B_PROJ, B_EPI, B_COUNT };
+enum { B_XFULL = 0, B_XEMPTY, B_WQFULL, B_WQEMPTY, B_WPFULL, B_WPEMPTY, B_QKV, B_QKR, B_S, B_PR, B_O, B_AOR, B_PROJ, B_EPI, B_COUNT };
 
 struct WmsaP {
   int B, H, W, shift, num_tiles, nW, wpr;  // wpr = windows per row (W/8)
@@ -88,7 +94,7 @@ __device__ __forceinline__ void store_row64(uint8_t* tile, int r, const float* v
     *reinterpret_cast<uint4*>(tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = pack8(v + 8 * j);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWq,
                const __grid_constant__ CUtensorMap mapWp, const WmsaP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -99,12 +105,12 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   float* lnc = reinterpret_cast<float*>(smem + OFF_LN);
   int* rid_s = reinterpret_cast<int*>(smem + OFF_RID);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapX);
     prefetch_tmap(&mapWq);
     prefetch_tmap(&mapWp);
-    const int counts[B_COUNT] = {1, 1, 1, 1, 4, 1, 4, 1, 4, 1, 4};
+    const int counts[B_COUNT] = {1, 1, 1, 1, 1, 1, 1, 4, 1, 4, 1, 4, 1, 4};
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
     fence_barrier_init();
   }
@@ -126,80 +132,92 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      // resident weights
-      mbar_expect_tx(&bar[B_WFULL], NH * 2 * WQ_TILE + NH * WP_TILE);
-      for (int h = 0; h < NH; ++h) {
-        for (int c = 0; c < 2; ++c)
-          for (int part = 0; part < 3; ++part)
-            tma_load_2d(smem + OFF_WQ + (h * 2 + c) * WQ_TILE + part * 32 * 128, &mapWq, &bar[B_WFULL], c * 64,
-                        part * C + h * 32);
-        tma_load_2d(smem + OFF_WP + h * WP_TILE, &mapWp, &bar[B_WFULL], h * 32, 0);
-      }
       const int s4 = p.shift >> 2, wq = p.W >> 2, hq = p.H >> 2;
-      uint32_t it = 0;
+      uint32_t it = 0, hc = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);
-        mbar_expect_tx(&bar[B_XFULL], 2 * X_CHUNK);
+        mbar_expect_tx(&bar[B_XFULL], 3 * X_CHUNK);
         for (int wt = 0; wt < 2; ++wt) {
           const int gw = 2 * tile + wt, b = gw / p.nW, wl = gw % p.nW, wi = wl / p.wpr, wj = wl % p.wpr;
           for (int quad = 0; quad < 4; ++quad) {
             const int yq = (2 * wi + (quad >> 1) + s4) % hq, xq = (2 * wj + (quad & 1) + s4) % wq;
-            for (int c = 0; c < 2; ++c)
-              tma_load_5d(smem + OFF_X + c * X_CHUNK + (wt * 64 + quad * 16) * 128, &mapX, &bar[B_XFULL], c * 64, 0, xq,
+            for (int c = 0; c < 3; ++c)
+              tma_load_5d(smem + OFF_X + c * X_CHUNK + (wt * 64 + quad * 16) * 64, &mapX, &bar[B_XFULL], c * 32, 0, xq,
                           0, b * hq + yq);
           }
+        }
+        // weights of each head: the slots are released by the MMA warp as soon as the MMAs reading them have completed
+        for (int h = 0; h < NH; ++h, ++hc) {
+          mbar_wait(&bar[B_WQEMPTY], (hc & 1) ^ 1);
+          mbar_expect_tx(&bar[B_WQFULL], 3 * WQ_CHUNK);
+          for (int c = 0; c < 3; ++c)
+            for (int part = 0; part < 3; ++part)
+              tma_load_2d(smem + OFF_WQ + c * WQ_CHUNK + part * 32 * 64, &mapWq, &bar[B_WQFULL], c * 32, part * C + h * 32);
+          mbar_wait(&bar[B_WPEMPTY], (hc & 1) ^ 1);
+          mbar_expect_tx(&bar[B_WPFULL], WP_TILE);
+          tma_load_2d(smem + OFF_WP, &mapWp, &bar[B_WPFULL], h * 32, 0);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t HI128 = desc_hi(128, 1024), HI64 = desc_hi(64, 512);
-      const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, 128);
-      const uint32_t id_pv = make_idesc_bf16(128, 32) | (1u << 16);  // B (= v_h) is MN-major
-      const uint32_t x_lo = desc_lo(smem_u32(smem + OFF_X)), wq_lo = desc_lo(smem_u32(smem + OFF_WQ));
-      const uint32_t wp_lo = desc_lo(smem_u32(smem + OFF_WP)), q_lo = desc_lo(smem_u32(smem + OFF_Q));
-      const uint32_t k_lo = desc_lo(smem_u32(smem + OFF_K)), v_lo = desc_lo(smem_u32(smem + OFF_V));
-      const uint32_t p_lo = desc_lo(smem_u32(smem + OFF_P)), ao_lo = desc_lo(smem_u32(smem + OFF_AO));
-      mbar_wait(&bar[B_WFULL], 0);
-      tc_fence_after();
-      uint32_t it = 0, hc = 0;  // tiles / heads processed by this CTA
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(&bar[B_XFULL], it & 1);
+    // the whole warp runs the loop (uniform control flow); one elected lane issues each batch of MMAs
+    constexpr uint32_t HI128 = desc_hi(128, 1024), HI64 = desc_hi(64, 512);
+    const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, 128);
+    const uint32_t id_pv = make_idesc_bf16(128, 32) | (1u << 16);  // B (= v_h) is MN-major
+    const uint32_t x_lo = desc_lo(smem_u32(smem + OFF_X)), wq_lo = desc_lo(smem_u32(smem + OFF_WQ));
+    const uint32_t wp_lo = desc_lo(smem_u32(smem + OFF_WP)), q_lo = desc_lo(smem_u32(smem + OFF_Q));
+    const uint32_t k_lo = desc_lo(smem_u32(smem + OFF_K)), v_lo = desc_lo(smem_u32(smem + OFF_V));
+    const uint32_t p_lo = desc_lo(smem_u32(smem + OFF_P)), ao_lo = desc_lo(smem_u32(smem + OFF_AO));
+    uint32_t it = 0, hc = 0;  // tiles / heads processed by this CTA
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(&bar[B_XFULL], it & 1);
+      for (int h = 0; h < NH; ++h, ++hc) {
+        const uint32_t hp = hc & 1;
+        // region A is free: the row threads finished reading O of the previous head (B_AOR waited below)
+        mbar_wait(&bar[B_WQFULL], hp);
         tc_fence_after();
-        for (int h = 0; h < NH; ++h, ++hc) {
-          const uint32_t hp = hc & 1;
-          // region A is free: the row threads finished reading O of the previous head (B_AOR waited below)
+        if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < 6; ++s) {  // K = 96: chunk 0 (4 steps) + first half of chunk 1
-            const uint32_t c = s >> 2, k = s & 3;
-            umma_bf16_w(tmem_a, x_lo + (c * X_CHUNK >> 4) + 2 * k, HI128,
-                        wq_lo + (((h * 2 + c) * WQ_TILE) >> 4) + 2 * k, HI128, id_qkv, s != 0);
+          for (int s = 0; s < 6; ++s) {  // K = 96: three 32-channel chunks x two K steps
+            const uint32_t c = s >> 1, k = s & 1;
+            umma_bf16_w(tmem_a, x_lo + (c * X_CHUNK >> 4) + 2 * k, HI64, wq_lo + (c * WQ_CHUNK >> 4) + 2 * k, HI64, id_qkv,
+                        s != 0);
           }
           umma_commit(&bar[B_QKV]);
+          umma_commit(&bar[B_WQEMPTY]);
           if (h == NH - 1) umma_commit(&bar[B_XEMPTY]);
-          mbar_wait(&bar[B_QKR], hp);
-          tc_fence_after();
+        }
+        __syncwarp();
+        mbar_wait(&bar[B_QKR], hp);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) umma_bf16_w(tmem_a, q_lo + 2 * k, HI64, k_lo + 2 * k, HI64, id_s, k != 0);
           umma_commit(&bar[B_S]);
-          mbar_wait(&bar[B_PR], hp);
-          tc_fence_after();
+        }
+        __syncwarp();
+        mbar_wait(&bar[B_PR], hp);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int s = 0; s < 8; ++s)  // 128 keys: A = P chunk s/4 (K-major), B = v rows 16s.. (MN-major, 64 B rows)
             umma_bf16_w(tmem_a, p_lo + ((s >> 2) * (P_CHUNK >> 4)) + 2 * (s & 3), HI128, v_lo + s * (1024 >> 4), HI64,
                         id_pv, s != 0);
           umma_commit(&bar[B_O]);
-          mbar_wait(&bar[B_AOR], hp);
-          tc_fence_after();
-          if (h == 0) {
-            mbar_wait(&bar[B_EPI], (it & 1) ^ 1);  // previous tile's epilogue has drained the proj accumulator
-            tc_fence_after();
-          }
+        }
+        __syncwarp();
+        mbar_wait(&bar[B_AOR], hp);
+        if (h == 0) mbar_wait(&bar[B_EPI], (it & 1) ^ 1);  // previous tile's epilogue has drained the proj accumulator
+        mbar_wait(&bar[B_WPFULL], hp);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            umma_bf16_w(tmem_proj, ao_lo + 2 * k, HI64, wp_lo + ((h * WP_TILE) >> 4) + 2 * k, HI64, id_qkv, (h | k) != 0);
+            umma_bf16_w(tmem_proj, ao_lo + 2 * k, HI64, wp_lo + 2 * k, HI64, id_qkv, (h | k) != 0);
+          umma_commit(&bar[B_WPEMPTY]);
           if (h == NH - 1) umma_commit(&bar[B_PROJ]);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -361,13 +379,13 @@ void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* r
   CUtensorMap mapX, mapWq, mapWp;
   uint64_t dx[5] = {(uint64_t)C, 4, (uint64_t)W / 4, 4, (uint64_t)B * H / 4};
   uint64_t sx[4] = {(uint64_t)C * 2, (uint64_t)4 * C * 2, (uint64_t)W * C * 2, (uint64_t)4 * W * C * 2};
-  uint32_t bx[5] = {64, 4, 1, 4, 1};
+  uint32_t bx[5] = {32, 4, 1, 4, 1};
   uint64_t dq[2] = {(uint64_t)C, (uint64_t)3 * C};
   uint64_t sq[1] = {(uint64_t)C * 2};
-  uint32_t bq[2] = {64, 32};
+  uint32_t bq[2] = {32, 32};
   uint64_t dp[2] = {(uint64_t)C, (uint64_t)C};
   uint32_t bp[2] = {32, 96};
-  if (!encode_tmap(&mapX, x, 5, dx, sx, bx, 128) || !encode_tmap(&mapWq, w.qkv_ln.w_tc, 2, dq, sq, bq, 128) ||
+  if (!encode_tmap(&mapX, x, 5, dx, sx, bx, 64) || !encode_tmap(&mapWq, w.qkv_ln.w_tc, 2, dq, sq, bq, 64) ||
       !encode_tmap(&mapWp, w.proj.w_tc, 2, dp, sq, bp, 64)) {
     snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_wmsa)");
     c.fail(SJ_ECUDA);
@@ -385,7 +403,7 @@ void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* r
     c.fail(SJ_ECUDA);
     return;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int grid = p.num_tiles < 2 * num_sms() ? p.num_tiles : 2 * num_sms();  // two CTAs per SM
   SJ_LAUNCH(c, "tc_wmsa", tc_wmsa_kernel, grid, NTHREADS, smem, mapX, mapWq, mapWp, p);
 }
 
