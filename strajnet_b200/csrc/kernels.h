@@ -176,6 +176,8 @@ void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, 
 // FG-MSA offset network (FG_MSA.py:84-92, :114-117, :134): q rows [B*256, ldq] (first 384 columns)
 // -> off fp32 [B,8,256,2] (8*tanh), pos = off + (j,i)
 void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos);
+// bf16 warp-MMA variant (fg_offset_mma.cu); returns false when not applicable
+bool fg_offset_mma(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos);
 // flow_hidden [B,8,256,384] = off . Wp2 + bp2 (FG_MSA.py:120-123)
 void fg_flow_hidden(Ctx& c, const float* off, const SjFgmsaW* w, int B, void* out);
 // query [B,8,256,384] = q2[b,l,:] (+ off . Wp2 + bp2 if fg)   (modules.py:827-831)

@@ -1,5 +1,7 @@
 // Index maps, data reshuffles, patch embedding, FG-MSA offset network, trajectory glue and the
 // decoder head.  All HBM-/latency-bound CUDA-core work.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sj {
@@ -598,6 +600,8 @@ void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, 
 
 void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {
   if (!c.ok() || c.dry) return;
+  static const bool mma_off = getenv("SJ_DISABLE_FG_OFFSET_MMA") != nullptr;
+  if (c.dtype == SJ_BF16 && !mma_off && fg_offset_mma(c, q, ldq, w, B, off, pos)) return;
   if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<bf16>, B * 32, 384, 0, (const bf16*)q, ldq, *w, off, pos);
   else SJ_LAUNCH(c, "fg_offset", fg_offset_kernel<float>, B * 32, 384, 0, (const float*)q, ldq, *w, off, pos);
 }
