@@ -26,9 +26,14 @@ CFG256 = dict(input_size=(256, 256), window_size=8, embed_dim=96, depths=[2, 2, 
 GFLOP_PER_FRAME = 200.75          # nominal, reference formulation, cfg256 + FG-MSA
 METRIC = "occupancy_flow_frames_per_sec"
 UNIT = "frames/s"
-# nominal FLOPs of the dominant kernel per frame: upconv 96->48 @256^2 x 8 waypoints, ONE of the two heads
+# dominant kernel: the 96->48 up-convolution @256^2 x 8 waypoints (tc_upconv4_kernel), ONE of its two launches per step.
+# Algorithmic FLOPs per frame: nominal = the reference's formulation (nearest x2 upsample + 3x3 conv, 9 taps per
+# output pixel); executed = after the exact sub-pixel folding (4 taps per output pixel).
 PROBE_ROLE = "dec.upconv3"
-PROBE_GFLOP_PER_FRAME = 2 * 8 * 65536 * 9 * 96 * 48 / 1e9
+PROBE_GFLOP_PER_FRAME_NOMINAL = 2 * 8 * 65536 * 9 * 96 * 48 / 1e9
+PROBE_GFLOP_PER_FRAME = 2 * 8 * 65536 * 4 * 96 * 48 / 1e9
+# DRAM bytes of that launch at batch 16 from `ncu --set full` (profiles/r01d_ncu_full_tc_kernels.md): read + write
+PROBE_DRAM_BYTES_B16 = 403.2e6 + 751.5e6
 
 
 def synth_inputs(B, S=256, seed=0):
@@ -306,10 +311,18 @@ def main():
         if pn.value > 0:
             per_launch_ms = pms.value / pn.value
             ach = PROBE_GFLOP_PER_FRAME * B / per_launch_ms  # GFLOP / ms = TFLOP/s
-            roof = {"bound": "tensor", "kernel": PROBE_ROLE, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src + ", sustained bf16",
+            ach_nom = PROBE_GFLOP_PER_FRAME_NOMINAL * B / per_launch_ms
+            peak_burst = peaks.get("bf16_tflops", 1590.0)
+            roof = {"bound": "tensor", "kernel": PROBE_ROLE + " (tc_upconv4_kernel)", "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": PROBE_DRAM_BYTES_B16 * B / 16 if args.dtype == "bf16" else None,
+                    "peak_source": peak_src + ", sustained bf16 (kernel timed inside the step)",
                     "launch_ms": per_launch_ms, "launches_timed": pn.value,
+                    "flops_counted": "executed = algorithmic after the exact sub-pixel folding (4 of 9 taps per output pixel)",
                     "algorithmic_gflop_per_launch": PROBE_GFLOP_PER_FRAME * B,
+                    "frac_of_burst_peak": ach / peak_burst,
+                    "nominal_gflop_per_launch": PROBE_GFLOP_PER_FRAME_NOMINAL * B, "nominal_tflops": ach_nom,
+                    "algorithmic_dram_bytes_per_launch": (128 * 128 * 96 + 256 * 256 * 48) * 2 * 8 * B,
                     "forward_nominal_tflops": fps / world * GFLOP_PER_FRAME / 1e3,
                     "forward_nominal_frac": fps / world * GFLOP_PER_FRAME / 1e3 / peak_tf}
         cpu = None
