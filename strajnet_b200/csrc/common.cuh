@@ -23,6 +23,11 @@ struct TlsState {
   int probe_n = 0;
   cudaEvent_t probe_ev[2 * kMaxProbe] = {};
   bool probe_ev_ready = false;
+  // fork/join helper stream of the whole-model forward (actor branch of the trajectory stack runs beside the raster
+  // encoder); created lazily per host thread and device, never destroyed
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int side_device = -1;
 };
 TlsState& tls();
 
