@@ -161,8 +161,9 @@ void patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, 
 }
 
 // ---- BasicLayer.call (modules.py:351-364) -------------------------------------------------------
+// in_mean/in_rstd (optional): norm1 statistics of x emitted by its producer
 void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBasicLayerW& w, const void* add, int B,
-                      int H, int W, int ws) {
+                      int H, int W, int ws, const float* in_mean = nullptr, const float* in_rstd = nullptr) {
   const int C = w.dim;
   const long long n = (long long)B * H * W * C;
   if (w.depth < 1 || !w.blocks_host || !res) { c.fail(SJ_EINVAL); return; }
@@ -174,16 +175,22 @@ void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBa
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 2; ++j) st[i][j] = (float*)c.alloc((size_t)B * H * W * 4);
   const int sh = (H <= ws || W <= ws) ? 0 : ws / 2;
-  window_token_map(c, H, W, ws, 0, maps[0]);
-  window_token_map(c, H, W, ws, sh, maps[1]);
+  // the fused window-MSA kernel derives the partition from TMA coordinates: no token maps needed
+  const bool all_fused = c.dtype == SJ_BF16 && getenv("SJ_DISABLE_FUSED_WMSA") == nullptr && w.blocks_host[0].qkv_ln.w_tc &&
+                         tc_wmsa_supported(B, H, W, C, w.heads, ws, 0) && tc_wmsa_supported(B, H, W, C, w.heads, ws, sh);
+  if (!all_fused) {
+    window_token_map(c, H, W, ws, 0, maps[0]);
+    window_token_map(c, H, W, ws, sh, maps[1]);
+  }
   const void* cur = x;
   bool have = false;
   for (int i = 0; i < w.depth; ++i) {
     void* dst = ((w.depth - 1 - i) % 2 == 0) ? res : tmp;
     int shift = (i % 2 == 0) ? 0 : sh;  // modules.py:331-332
     const bool want = i + 1 < w.depth;
-    have = swin_block_impl(c, cur, dst, w.blocks_host[i], B, H, W, C, w.heads, ws, shift, maps[i % 2],
-                           have ? st[(i + 1) % 2][0] : nullptr, have ? st[(i + 1) % 2][1] : nullptr,
+    const float* rm = i == 0 ? in_mean : (have ? st[(i + 1) % 2][0] : nullptr);
+    const float* rr = i == 0 ? in_rstd : (have ? st[(i + 1) % 2][1] : nullptr);
+    have = swin_block_impl(c, cur, dst, w.blocks_host[i], B, H, W, C, w.heads, ws, shift, maps[i % 2], rm, rr,
                            want ? st[i % 2][0] : nullptr, want ? st[i % 2][1] : nullptr);
     cur = dst;
   }
@@ -213,6 +220,10 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   }
   void* f0 = c.alloc_act(B * L0 * E);
   void* flow_x = c.alloc_act(B * L0 / 4 * 2 * E);
+  // norm1 statistics of the first block of each 96-channel layer, emitted by the patch-embedding combine kernel
+  float* pe_mean = (float*)c.alloc((size_t)B * L0 * 4);
+  float* pe_rstd = (float*)c.alloc((size_t)B * L0 * 4);
+  bool pe_stats = false;
   // bf16 mode: the 4x4/s4 patch convs run as tcgen05 GEMMs over an im2col'ed bf16 matrix
   const bool pe_tc = c.dtype == SJ_BF16 && w.pe_vec.proj.w_tc && w.pe_map.proj.w_tc && w.pe_flow.proj.w_tc;
   auto embed_tc = [&](const void* img, int itype, int Simg, int Cin, int es, const SjPatchEmbedW& pw, void* conv_out) {
@@ -230,7 +241,8 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     void* cf = c.alloc_act(B * L0 * E);
     embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
     SjNorm none{};
-    pe_combine(c, cf, nullptr, B, P, 0, w.pe_flow.norm, none, w.flow_norm, f0);
+    pe_combine(c, cf, nullptr, B, P, 0, w.pe_flow.norm, none, w.flow_norm, f0, pe_mean, pe_rstd);
+    pe_stats = true;
   } else {  // patch_embed_flow -> flow_norm (modules.py:576-577)
     PatchEmbedP p;
     p.img[0] = flow; p.Cin[0] = 2; p.es[0] = 1; p.S[0] = S;
@@ -238,14 +250,15 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     p.n_in = 1; p.gf = w.flow_norm.g; p.bf = w.flow_norm.b; p.y = f0; p.B = B; p.E = E;
     patch_embed(c, p);
   }
-  basic_layer_impl(c, f0, flow_x, full[0], w.flow_layer, nullptr, B, P, P, 8);
+  basic_layer_impl(c, f0, flow_x, full[0], w.flow_layer, nullptr, B, P, P, 8, pe_stats ? pe_mean : nullptr,
+                   pe_stats ? pe_rstd : nullptr);
   void* x0 = f0;  // f0 is dead once the flow layer has run
   if (pe_tc) {
     void* cv = c.alloc_act(B * L0 * E);
     void* cm = c.alloc_act((size_t)B * 4096 * E);
     embed_tc(ogm, ogm_type, S, 11, 2, w.pe_vec, cv);
     embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
-    pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, x0);
+    pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, x0, pe_mean, pe_rstd);
   } else {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
     PatchEmbedP p;
     p.img[0] = ogm; p.itype[0] = ogm_type; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
@@ -258,7 +271,8 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   }
   void* x1 = c.alloc_act(B * L0 / 4 * 2 * E);
   void* x2 = c.alloc_act(B * L0 / 16 * 4 * E);
-  basic_layer_impl(c, x0, x1, full[1], w.layers[0], flow_x, B, P, P, 8);  // + flow_x (modules.py:613)
+  basic_layer_impl(c, x0, x1, full[1], w.layers[0], flow_x, B, P, P, 8, pe_stats ? pe_mean : nullptr,
+                   pe_stats ? pe_rstd : nullptr);  // + flow_x (modules.py:613)
   basic_layer_impl(c, x1, x2, full[2], w.layers[1], nullptr, B, P / 2, P / 2, 8);
   basic_layer_impl(c, x2, nullptr, full[3], w.layers[2], nullptr, B, P / 4, P / 4, 8);
   if (large) {  // centre crops (modules.py:614-622)

@@ -170,8 +170,9 @@ struct PatchEmbedP {
 void patch_embed(Ctx& c, const PatchEmbedP& p);
 // bf16 tensor-core variant: im2col to a bf16 matrix (then tc_gemm), and the LN / sum / LN combine
 void im2col4(Ctx& c, const void* img, int itype, int B, int S, int Cin, int es, int Kpad, void* A);
+// st_mean/st_rstd (optional): eps-1e-5 LayerNorm statistics of the output rows (norm1 of the first Swin block)
 void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, const SjNorm& n0, const SjNorm& n1,
-                const SjNorm& nf, void* y);
+                const SjNorm& nf, void* y, float* st_mean = nullptr, float* st_rstd = nullptr);
 
 // FG-MSA offset network (FG_MSA.py:84-92, :114-117, :134): q rows [B*256, ldq] (first 384 columns)
 // -> off fp32 [B,8,256,2] (8*tanh), pos = off + (j,i)

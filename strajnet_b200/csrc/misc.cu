@@ -216,7 +216,8 @@ __global__ void im2col4_kernel(const void* __restrict__ img, int itype, int B, i
 // c1 is optional and may cover only the centre P1 x P1 tokens of the P x P grid (pad1 = (P - P1)/2), contributing 0
 // elsewhere.  One warp per token, 3 channels per lane.
 __global__ void pe_combine_kernel(const bf16* __restrict__ c0, const bf16* __restrict__ c1, int B, int P, int pad1,
-                                  SjNorm n0, SjNorm n1, SjNorm nf, bf16* __restrict__ y) {
+                                  SjNorm n0, SjNorm n1, SjNorm nf, bf16* __restrict__ y, float* __restrict__ st_mean,
+                                  float* __restrict__ st_rstd) {
   const long long tok = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (tok >= (long long)B * P * P) return;
@@ -245,7 +246,20 @@ __global__ void pe_combine_kernel(const bf16* __restrict__ c0, const bf16* __res
   }
   ln3(a, nf);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) y[tok * 96 + lane + 32 * j] = __float2bfloat16_rn(a[j]);
+  for (int j = 0; j < 3; ++j) {
+    const bf16 r = __float2bfloat16_rn(a[j]);
+    y[tok * 96 + lane + 32 * j] = r;
+    a[j] = __bfloat162float(r);
+  }
+  if (st_mean) {  // eps-1e-5 LayerNorm statistics of the stored row: norm1 of the first Swin block
+    const float mu = warp_sum(a[0] + a[1] + a[2]) / 96.f;
+    const float d0 = a[0] - mu, d1 = a[1] - mu, d2 = a[2] - mu;
+    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) / 96.f;
+    if (lane == 0) {
+      st_mean[tok] = mu;
+      st_rstd[tok] = rsqrtf(var + 1e-5f);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- FG-MSA offset network
@@ -591,11 +605,11 @@ void im2col4(Ctx& c, const void* img, int itype, int B, int S, int Cin, int es, 
   SJ_LAUNCH(c, "im2col4", im2col4_kernel, cdiv(n, 256), 256, 0, img, itype, B, S, Cin, es, Kpad, (bf16*)A);
 }
 void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, const SjNorm& n0, const SjNorm& n1,
-                const SjNorm& nf, void* y) {
+                const SjNorm& nf, void* y, float* st_mean, float* st_rstd) {
   if (!c.ok() || c.dry) return;
   const long long ntok = (long long)B * P * P;
   SJ_LAUNCH(c, "pe_combine", pe_combine_kernel, cdiv(ntok, 8), 256, 0, (const bf16*)c0, (const bf16*)c1, B, P, pad1, n0, n1,
-            nf, (bf16*)y);
+            nf, (bf16*)y, st_mean, st_rstd);
 }
 
 void fg_offset(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {
