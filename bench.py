@@ -165,6 +165,11 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE JSON line: anything native libraries print there (e.g. "NCCL version ...") is sent to
+    # stderr by pointing fd 1 at fd 2 for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch.distributed as dist
     import strajnet_b200 as sj
@@ -352,7 +357,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
