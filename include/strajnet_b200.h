@@ -159,6 +159,12 @@ long long sj_launch_count(int reset);
 /* of which tcgen05 (tensor-core) kernels */
 long long sj_tc_launch_count(int reset);
 
+/* Host-side helper of the record / checkpoint readers (scope rows f2, f3): CRC-32C (Castagnoli) of `n` bytes,
+ * continuing from `crc` (0 to start).  This is the checksum of the TFRecord framing the reference reads through
+ * tf.data.TFRecordDataset (inference.py:256-258, train.py:380-388) and of TF tensor-bundle checkpoints
+ * (model.load_weights, inference.py:283).  Pure host code: no GPU needed. */
+uint32_t sj_crc32c(const void* data, size_t n, uint32_t crc);
+
 /* Opt-in timing probe for bench.py: CUDA events (created lazily by the library; the one exception to
  * "allocates nothing") are recorded on the launching stream around every kernel launched by this thread
  * whose forward step name starts with `role_prefix` ("enc", "fgmsa", "traj", "dec.upconv3", ...).

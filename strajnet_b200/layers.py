@@ -73,9 +73,23 @@ class Layer:
         return dict(self.weights)
 
     def save_weights(self, path: str) -> None:
-        np.savez(path, **{k: v.numpy() for k, v in self.get_weights().items()})
+        """Keras semantics (train.py:358,366): a path without suffix is a TF-format checkpoint prefix
+        (`<path>.index` + `<path>.data-00000-of-00001`, written by tf_checkpoint.py); `*.npz` saves a NumPy archive."""
+        w = {k: v.numpy() for k, v in self.get_weights().items()}
+        if path.endswith(".npz"):
+            np.savez(path, **w)
+        else:
+            from . import tf_checkpoint
+            tf_checkpoint.save_keras_checkpoint(path, w)
 
     def load_weights(self, path: str) -> None:
+        """`model.load_weights(path)` (inference.py:283): TF-format checkpoint prefix, or a `.npz` archive keyed by the
+        attribute paths of SURVEY App. B.  Every parameter of the model must be present (KeyError otherwise)."""
+        from . import tf_checkpoint
+        if not path.endswith(".npz") and tf_checkpoint.is_tf_checkpoint(path):
+            w = tf_checkpoint.load_keras_checkpoint(path, sorted(self.weight_shapes()))
+            self.set_weights({k: torch.from_numpy(v) for k, v in w.items()})
+            return
         with np.load(path if path.endswith(".npz") else path + ".npz") as z:
             self.set_weights({k: torch.from_numpy(z[k]) for k in z.files})
 

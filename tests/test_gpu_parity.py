@@ -355,3 +355,40 @@ def test_pipeline_raw_quantised(sj):
     ref = m.predict_quantized(ogm_u8, map_i8, inp["obs"], inp["occ"], inp["flow"]).cpu()
     for y in outs:
         assert torch.equal(y, ref)
+
+
+def test_records_to_model_bit_identical(sj, tmp_path):
+    """f3 end to end: TFRecord file -> framing -> Example -> record decode (strajnet_b200/records.py) -> model.  The raw
+    record dtypes (bool ogm, int8 map) fed straight to the device give the same logits, bit for bit, as the reference's
+    float32 decode (inference.py:84-96); config = the reference's inference config (512 input, inference.py:142)."""
+    from strajnet_b200 import records as R
+    from tests.test_records import _synthetic_example
+    path = str(tmp_path / "scenes.tfrecords")
+    R.write_tfrecords(path, [_synthetic_example(s)[1] for s in (11, 12)])
+    recs = list(R.read_tfrecords(path))
+    raw = R.batch_examples([R.decode_example(r, raw=True) for r in recs])
+    ref = R.batch_examples([R.decode_example(r, raw=False) for r in recs])
+    assert raw["scenario/id"] == [b"scene11", b"scene12"]
+    w = O.make_weights(O.CFG512, seed=0)
+    m = sj.STrajNet(O.CFG512, fg_msa=True, fg=True, large_ogm=True, dtype="bfloat16")
+    m.set_weights(w)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    y_raw = m(t(raw["ogm"]), t(raw["map_img"]), training=False, obs=t(raw["obs"]), occ=t(raw["occ"]), mapt=t(raw["mapt"]), flow=t(raw["flow"]))
+    y_ref = m(t(ref["ogm"]), t(ref["map_img"]), training=False, obs=t(ref["obs"]), occ=t(ref["occ"]), mapt=t(ref["mapt"]), flow=t(ref["flow"]))
+    assert y_raw.shape == (2, 256, 256, 32) and torch.isfinite(y_raw).all()
+    assert torch.equal(y_raw, y_ref)
+
+
+def test_strajnet_tf_checkpoint_roundtrip(sj, tmp_path):
+    """f2: `save_weights(prefix)` writes a TF-format checkpoint (tensor bundle + object graph), `load_weights(prefix)` on a
+    fresh model restores every parameter by attribute path; the two models agree bit for bit."""
+    from strajnet_b200 import tf_checkpoint as T
+    m = _model(sj)
+    prefix = str(tmp_path / "final_model")
+    m.save_weights(prefix)
+    b = T.TensorBundle(prefix)
+    assert len(b.variables_by_attribute_path()) == len(m.get_weights()) == 299
+    m2 = sj.STrajNet(O.CFG256, fg_msa=True, fg=True, large_ogm=False)
+    m2.load_weights(prefix)
+    inp = O.make_inputs(1, 256, seed=41)
+    assert torch.equal(_fwd(m, inp), _fwd(m2, inp))
