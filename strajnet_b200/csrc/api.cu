@@ -123,20 +123,28 @@ bool swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
     gemm(c, g);
   }
   if (!have_stats2) ln_stats(c, x1, (int)M, C, C, 1e-5f, mean2, rstd2);
-  {  // norm2 -> fc1 -> GELU   (modules.py:260, :41-42)
-    GemmP g;
-    g.A = x1; g.lda = C; g.set_weights(w.fc1); g.ldw = 4 * C; g.C = hbuf; g.ldc = 4 * C;
-    g.M = (int)M; g.N = 4 * C; g.K = C; g.act = ACT_GELU;
-    g.ln_mean = mean2; g.ln_rstd = rstd2; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
-    gemm(c, g);
-  }
   bool wrote = false;
-  {  // fc2 + residual
-    GemmP g;
-    g.A = hbuf; g.lda = 4 * C; g.set_weights(w.fc2); g.ldw = C; g.C = y; g.ldc = C;
-    g.M = (int)M; g.N = C; g.K = 4 * C; g.R = x1; g.ldr = C;
-    if (out_mean && stats_fused) { g.st_mean = out_mean; g.st_rstd = out_rstd; g.st_eps = 1e-5f; wrote = true; }
-    gemm(c, g);
+  static const bool mlp_off = getenv("SJ_DISABLE_FUSED_MLP") != nullptr;
+  if (c.dtype == SJ_BF16 && !mlp_off && tc_mlp96_supported(C, 4 * C, w)) {
+    // norm2 -> fc1 -> GELU -> fc2 -> + residual as one kernel, hidden activations kept on the SM (tc_mlp.cu)
+    const bool want = out_mean && stats_fused;
+    tc_mlp96(c, x1, y, mean2, rstd2, w, (int)M, want ? out_mean : nullptr, want ? out_rstd : nullptr);
+    wrote = want;
+  } else {
+    {  // norm2 -> fc1 -> GELU   (modules.py:260, :41-42)
+      GemmP g;
+      g.A = x1; g.lda = C; g.set_weights(w.fc1); g.ldw = 4 * C; g.C = hbuf; g.ldc = 4 * C;
+      g.M = (int)M; g.N = 4 * C; g.K = C; g.act = ACT_GELU;
+      g.ln_mean = mean2; g.ln_rstd = rstd2; g.ln_g = w.norm2.g; g.ln_b = w.norm2.b;
+      gemm(c, g);
+    }
+    {  // fc2 + residual
+      GemmP g;
+      g.A = hbuf; g.lda = 4 * C; g.set_weights(w.fc2); g.ldw = C; g.C = y; g.ldc = C;
+      g.M = (int)M; g.N = C; g.K = 4 * C; g.R = x1; g.ldr = C;
+      if (out_mean && stats_fused) { g.st_mean = out_mean; g.st_rstd = out_rstd; g.st_eps = 1e-5f; wrote = true; }
+      gemm(c, g);
+    }
   }
   c.ws.release(mark);
   return wrote;
