@@ -2,13 +2,16 @@
 //   y = x + fc2( GELU( fc1( norm2(x) ) ) )                                   (modules.py:260-261 with Mlp.call :41-45)
 // as ONE kernel.  As two tcgen05 GEMMs (tc_gemm.cu) this half costs 53 us per block at batch 16, nearly all of it
 // epilogue and launch latency around a 50 MB hidden tensor that is written to HBM and read straight back; here the
-// hidden activations of a 128-token tile never leave the SM:
+// hidden activations of a 128-token tile never leave the SM (41 us per block; with an empty epilogue the kernel still
+// takes 31 us: at batch 16 there are only 3.5 tiles per SM and each tile is a chain of ~6 MMA <-> epilogue hand-offs,
+// and the 144 KB of resident weights leave room for one tile per SM, so the chain latency is what is left):
 //   * weights resident in shared memory: norm2-folded W1 [384 x 96] (72 KB) and W2 [96 x 384] (72 KB);
-//   * fc1 runs as two N = 192 halves into two TMEM accumulators (LayerNorm folded: raw tokens feed the MMA, the
+//   * fc1 runs as four N = 96 quarters into four TMEM accumulators (LayerNorm folded: raw tokens feed the MMA, the
 //     epilogue applies rstd * (acc - mean * colsum) + bias');
-//   * the 8 epilogue warps apply the fold + tanh-GELU and write each half as a bf16 A operand (128 x 192, 48 KB,
-//     SWIZZLE_128B) into shared memory; fc2 consumes it as K = 192 and accumulates both halves into a third TMEM
-//     accumulator (96 columns);
+//   * the 8 epilogue warps apply the fold + tanh-GELU and write each quarter as a bf16 A operand (128 x 96, 24 KB,
+//     32-unit SWIZZLE_64B chunks) into one of TWO shared-memory buffers; fc2 consumes it as K = 96 and accumulates the
+//     four quarters into a fifth TMEM accumulator (96 columns).  With two buffers the fc2 MMAs of quarter q run under
+//     the GELU of quarter q+1, and fc1 of the next tile under the output epilogue: the epilogue warps never wait;
 //   * final epilogue: + bias + residual, bf16 store, and (optionally) the eps-1e-5 LayerNorm statistics of the output
 //     rows for the next block's norm1.
 // Warp 0 = TMA producer, warp 1 = tcgen05.mma issue (uniform loop, elect.sync), warps 2..9 = epilogue (two warps per
@@ -23,24 +26,25 @@ namespace {
 
 using namespace tc;
 
-constexpr int C = 96, HID = 384, HH = HID / 2, NTHREADS = 320;
+constexpr int C = 96, HID = 384, HQ = HID / 4, NTHREADS = 320;
 constexpr int X_CHUNK = 128 * 64;           // 8 KB: 128 tokens x 32 channels (SWIZZLE_64B)
 constexpr int W1_CHUNK = HID * 64;          // 24 KB: 384 rows x 32 channels
-constexpr int W2_CHUNK = C * 128;           // 12 KB: 96 rows x 64 hidden units (SWIZZLE_128B)
-constexpr int H_CHUNK = 128 * 128;          // 16 KB: 128 tokens x 64 hidden units
+constexpr int W2_CHUNK = C * 64;            // 6 KB: 96 rows x 32 hidden units
+constexpr int H_CHUNK = 128 * 64;           // 8 KB: 128 tokens x 32 hidden units
+constexpr int H_BUF = 3 * H_CHUNK;          // one quarter of the hidden tile
 constexpr int OFF_X = 0;
 constexpr int OFF_W1 = OFF_X + 3 * X_CHUNK;
 constexpr int OFF_W2 = OFF_W1 + 3 * W1_CHUNK;
-constexpr int OFF_H = OFF_W2 + 6 * W2_CHUNK;
-constexpr int OFF_VEC = OFF_H + 3 * H_CHUNK;            // float colsum[384], bias1[384], bias2[96]
+constexpr int OFF_H = OFF_W2 + 12 * W2_CHUNK;
+constexpr int OFF_VEC = OFF_H + 2 * H_BUF;              // float colsum[384], bias1[384], bias2[96]
 constexpr int OFF_STAT = OFF_VEC + (2 * HID + C) * 4;   // float2 [128]
 constexpr int OFF_BAR = OFF_STAT + 128 * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(OFF_W2 % 1024 == 0 && OFF_H % 1024 == 0, "SWIZZLE_128B tiles must be 1024-byte aligned");
+static_assert(OFF_W2 % 1024 == 0 && OFF_H % 1024 == 0, "tile alignment");
 static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
-constexpr uint32_t TM_A = 0, TM_B = 192, TM_O = 384;    // TMEM columns: fc1 halves, fc2 output
+constexpr uint32_t TM_Q = 0, TM_O = 384;    // TMEM columns: four fc1 quarters (96 each), fc2 output
 
-enum { B_XFULL = 0, B_XEMPTY, B_WFULL, B_AFULL, B_BFULL, B_HA, B_FC2A, B_HB, B_OFULL, B_OEMPTY, B_COUNT };
+enum { B_XFULL = 0, B_XEMPTY, B_WFULL, B_Q0, B_Q1, B_Q2, B_Q3, B_HFULL0, B_HFULL1, B_HEMPTY0, B_HEMPTY1, B_OFULL, B_OEMPTY, B_COUNT };
 
 struct MlpP {
   int M, num_tiles;
@@ -72,7 +76,7 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     prefetch_tmap(&mapX);
     prefetch_tmap(&mapW1);
     prefetch_tmap(&mapW2);
-    const int counts[B_COUNT] = {1, 1, 1, 1, 1, 8, 1, 8, 1, 8};
+    const int counts[B_COUNT] = {1, 1, 1, 1, 1, 1, 1, 8, 8, 1, 1, 1, 8};
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
     fence_barrier_init();
   }
@@ -89,11 +93,11 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&bar[B_WFULL], 3 * W1_CHUNK + 6 * W2_CHUNK);
+      mbar_expect_tx(&bar[B_WFULL], 3 * W1_CHUNK + 12 * W2_CHUNK);
       for (int c = 0; c < 3; ++c)
         for (int hf = 0; hf < 2; ++hf)
-          tma_load_2d(smem + OFF_W1 + c * W1_CHUNK + hf * HH * 64, &mapW1, &bar[B_WFULL], c * 32, hf * HH);
-      for (int c = 0; c < 6; ++c) tma_load_2d(smem + OFF_W2 + c * W2_CHUNK, &mapW2, &bar[B_WFULL], c * 64, 0);
+          tma_load_2d(smem + OFF_W1 + c * W1_CHUNK + hf * 192 * 64, &mapW1, &bar[B_WFULL], c * 32, hf * 192);
+      for (int c = 0; c < 12; ++c) tma_load_2d(smem + OFF_W2 + c * W2_CHUNK, &mapW2, &bar[B_WFULL], c * 32, 0);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);
@@ -102,8 +106,8 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t HI128 = desc_hi(128, 1024), HI64 = desc_hi(64, 512);
-    const uint32_t id1 = make_idesc_bf16(128, HH), id2 = make_idesc_bf16(128, C);
+    constexpr uint32_t HI64 = desc_hi(64, 512);
+    const uint32_t idq = make_idesc_bf16(128, HQ);  // N = 96 for fc1 quarters and for fc2
     const uint32_t x_lo = desc_lo(smem_u32(smem + OFF_X)), w1_lo = desc_lo(smem_u32(smem + OFF_W1));
     const uint32_t w2_lo = desc_lo(smem_u32(smem + OFF_W2)), h_lo = desc_lo(smem_u32(smem + OFF_H));
     mbar_wait(&bar[B_WFULL], 0);
@@ -113,46 +117,39 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       mbar_wait(&bar[B_XFULL], ph);
       tc_fence_after();
       if (elect_one()) {
-        // fc1, two halves of 192 hidden units; K = 96 = three 32-channel chunks x two K steps
+        // fc1, four quarters of 96 hidden units; K = 96 = three 32-channel chunks x two K steps
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
           for (int s = 0; s < 6; ++s) {
             const uint32_t c = s >> 1, k = s & 1;
-            umma_bf16_w(tmem + (hf ? TM_B : TM_A), x_lo + (c * X_CHUNK >> 4) + 2 * k, HI64,
-                        w1_lo + ((c * W1_CHUNK + hf * HH * 64) >> 4) + 2 * k, HI64, id1, s != 0);
+            umma_bf16_w(tmem + TM_Q + q * HQ, x_lo + (c * X_CHUNK >> 4) + 2 * k, HI64,
+                        w1_lo + ((c * W1_CHUNK + q * HQ * 64) >> 4) + 2 * k, HI64, idq, s != 0);
           }
-          umma_commit(&bar[hf ? B_BFULL : B_AFULL]);
+          umma_commit(&bar[B_Q0 + q]);
         }
         umma_commit(&bar[B_XEMPTY]);
       }
       __syncwarp();
-      // fc2, first half: needs H_a in shared memory and the output accumulator drained by the previous tile
-      mbar_wait(&bar[B_HA], ph);
-      mbar_wait(&bar[B_OEMPTY], ph ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
+      // fc2: quarter q comes through hidden buffer q & 1 (each buffer is filled twice per tile)
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t use = 2 * it + (q >> 1);  // how often buffer q & 1 has been used before
+        mbar_wait(&bar[B_HFULL0 + (q & 1)], use & 1);
+        if (q == 0) mbar_wait(&bar[B_OEMPTY], ph ^ 1);  // output accumulator drained by the previous tile
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < 12; ++s) {
-          const uint32_t c = s >> 2, k = s & 3;
-          umma_bf16_w(tmem + TM_O, h_lo + (c * H_CHUNK >> 4) + 2 * k, HI128, w2_lo + (c * W2_CHUNK >> 4) + 2 * k, HI128, id2,
-                      s != 0);
+          for (int s = 0; s < 6; ++s) {
+            const uint32_t c = s >> 1, k = s & 1;
+            umma_bf16_w(tmem + TM_O, h_lo + (((q & 1) * H_BUF + c * H_CHUNK) >> 4) + 2 * k, HI64,
+                        w2_lo + ((3 * q + c) * W2_CHUNK >> 4) + 2 * k, HI64, idq, (q | s) != 0);
+          }
+          umma_commit(&bar[B_HEMPTY0 + (q & 1)]);
+          if (q == 3) umma_commit(&bar[B_OFULL]);
         }
-        umma_commit(&bar[B_FC2A]);
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(&bar[B_HB], ph);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int s = 0; s < 12; ++s) {
-          const uint32_t c = s >> 2, k = s & 3;
-          umma_bf16_w(tmem + TM_O, h_lo + (c * H_CHUNK >> 4) + 2 * k, HI128, w2_lo + ((3 + c) * W2_CHUNK >> 4) + 2 * k,
-                      HI128, id2, 1u);
-        }
-        umma_commit(&bar[B_OFULL]);
-      }
-      __syncwarp();
     }
   } else {
     const int quarter = warp % 4, half = (warp - 2) / 4;
@@ -173,37 +170,64 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 6; ++i) res[i] = *reinterpret_cast<const uint4*>(p.x + row * C + half * 48 + 8 * i);
       }
-      // ---- hidden halves: LN fold + GELU -> bf16 A operand of fc2 ----
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        mbar_wait(&bar[hf ? B_BFULL : B_AFULL], ph);
-        if (hf) mbar_wait(&bar[B_FC2A], ph);  // fc2 has finished reading H_a
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 3; ++cc) {
-          const int n0 = half * 96 + cc * 32;  // hidden unit within this half
-          float v[32];
-          tmem_ld32(tmem + lane_addr + (hf ? TM_B : TM_A) + n0, v);
-          const int ng = hf * HH + n0;         // global hidden unit
+      // ---- hidden quarters: LN fold + GELU -> bf16 A operand of fc2 (this thread: 48 of the 96 units) ----
+      // Software pipeline over 8 parts (quarter q = part / 2; part 0: units +0..31, part 1: units +32..47): the TMEM load
+      // of part i+1 is in flight while part i goes through the fold / GELU / shared-memory stores.
+      uint32_t ta[32], tb[32];
+      auto issue = [&](int part, uint32_t (&t)[32]) {
+        const int q = part >> 1;
+        const uint32_t tq = tmem + lane_addr + TM_Q + q * HQ + half * 48;
+        if (!(part & 1)) {
+          mbar_wait(&bar[B_Q0 + q], ph);
+          tc_fence_after();
+          tmem_ld32_issue(tq, t);
+        } else {
+          tmem_ld16_issue(tq + 32, t);
+        }
+      };
+      auto process = [&](int part, uint32_t (&t)[32]) {
+        const int q = part >> 1, sub = part & 1, cnt = sub ? 16 : 32;
+        const uint32_t use = 2 * it + (q >> 1);
+        if (!sub) mbar_wait(&bar[B_HEMPTY0 + (q & 1)], (use & 1) ^ 1);  // fc2 has finished reading the previous tenant
+        uint8_t* hbuf = smem + OFF_H + (q & 1) * H_BUF;
+        const int nl = half * 48 + sub * 32;  // quarter-local first hidden unit of this part
+        const int ng = q * HQ + nl;           // global hidden unit
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 32; i += 4) {
+          if (i < cnt) {
             const float4 c4 = *reinterpret_cast<const float4*>(cs + ng + i);
             const float4 d4 = *reinterpret_cast<const float4*>(b1 + ng + i);
-            v[i] = act_fast(rstd * (v[i] - mean * c4.x) + d4.x, ACT_GELU);
-            v[i + 1] = act_fast(rstd * (v[i + 1] - mean * c4.y) + d4.y, ACT_GELU);
-            v[i + 2] = act_fast(rstd * (v[i + 2] - mean * c4.z) + d4.z, ACT_GELU);
-            v[i + 3] = act_fast(rstd * (v[i + 3] - mean * c4.w) + d4.w, ACT_GELU);
+            v[i] = act_fast(rstd * (__uint_as_float(t[i]) - mean * c4.x) + d4.x, ACT_GELU);
+            v[i + 1] = act_fast(rstd * (__uint_as_float(t[i + 1]) - mean * c4.y) + d4.y, ACT_GELU);
+            v[i + 2] = act_fast(rstd * (__uint_as_float(t[i + 2]) - mean * c4.z) + d4.z, ACT_GELU);
+            v[i + 3] = act_fast(rstd * (__uint_as_float(t[i + 3]) - mean * c4.w) + d4.w, ACT_GELU);
           }
-          // 128-byte swizzled rows: chunk = n / 64, 16-byte unit u = (n % 64) / 8 lands at u ^ (row & 7)
-          uint8_t* hrow = smem + OFF_H + (n0 >> 6) * H_CHUNK + r * 128;
-          const int u0 = (n0 & 63) >> 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) st8_bf16(reinterpret_cast<bf16*>(hrow + (((u0 + j) ^ (r & 7)) << 4)), v + 8 * j);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[hf ? B_HB : B_HA]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (8 * j < cnt) {
+            const int n = nl + 8 * j;  // multiple of 8: one 16-byte unit of a 64-byte swizzled row
+            uint8_t* dst = hbuf + (n >> 5) * H_CHUNK + r * 64 + ((((n & 31) >> 3) ^ ((r >> 1) & 3)) << 4);
+            st8_bf16(reinterpret_cast<bf16*>(dst), v + 8 * j);
+          }
+        }
+        if (sub) {
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_HFULL0 + (q & 1)]);
+        }
+      };
+      issue(0, ta);
+#pragma unroll
+      for (int part = 0; part < 8; part += 2) {
+        tmem_ld_wait(ta);
+        issue(part + 1, tb);
+        process(part, ta);
+        tmem_ld_wait(tb);
+        if (part + 2 < 8) issue(part + 2, ta);
+        process(part + 1, tb);
       }
       // ---- output: + bias + residual, statistics, store ----
       mbar_wait(&bar[B_OFULL], ph);
@@ -276,12 +300,12 @@ void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* 
   uint64_t sx[1] = {(uint64_t)C * 2};
   uint32_t bx[2] = {32, 128};
   uint64_t d1[2] = {(uint64_t)C, (uint64_t)HID};
-  uint32_t b1[2] = {32, (uint32_t)HH};
+  uint32_t b1[2] = {32, 192};
   uint64_t d2[2] = {(uint64_t)HID, (uint64_t)C};
   uint64_t s2[1] = {(uint64_t)HID * 2};
-  uint32_t b2[2] = {64, (uint32_t)C};
+  uint32_t b2[2] = {32, (uint32_t)C};
   if (!encode_tmap(&mapX, x, 2, dx, sx, bx, 64) || !encode_tmap(&mapW1, w.fc1.w_tc, 2, d1, sx, b1, 64) ||
-      !encode_tmap(&mapW2, w.fc2.w_tc, 2, d2, s2, b2, 128)) {
+      !encode_tmap(&mapW2, w.fc2.w_tc, 2, d2, s2, b2, 64)) {
     snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_mlp96)");
     c.fail(SJ_ECUDA);
     return;
