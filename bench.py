@@ -229,15 +229,16 @@ def main():
     host_raw = dict(host)
     host_raw["ogm"] = (host["ogm"] != 0).to(torch.uint8).pin_memory()
     host_raw["map_img"] = torch.round(host["map_img"] * 256).to(torch.int8).pin_memory()
-    pipes = {"raw": (InferencePipeline(model, B, raw_inputs=True, quantized=True), host_raw),
-             "fp32": (InferencePipeline(model, B), host)}
+    depth = int(os.environ.get("SJ_E2E_DEPTH", "2"))
+    pipes = {"raw": (InferencePipeline(model, B, depth=depth, raw_inputs=True, quantized=True), host_raw),
+             "fp32": (InferencePipeline(model, B, depth=depth), host)}
     pipe, host_e2e = pipes["raw"]
     pending = []
 
     def step_e2e():
         pending.append(pipe.submit(host_e2e))
-        if len(pending) > 1:
-            pending.pop(0).result()  # consume batch i-1 while batch i runs
+        if len(pending) > depth - 1:
+            pending.pop(0).result()  # consume the oldest batch while the newer ones run
         if world > 1:
             with torch.cuda.stream(pipe.s_run):
                 gather_outputs(pipe.dev_out[(pipe.i - 1) % pipe.depth])
