@@ -32,7 +32,7 @@ UNIT = "frames/s"
 PROBE_ROLE = "dec.upconv3"
 PROBE_GFLOP_PER_FRAME_NOMINAL = 2 * 8 * 65536 * 9 * 96 * 48 / 1e9
 PROBE_GFLOP_PER_FRAME = 2 * 8 * 65536 * 4 * 96 * 48 / 1e9
-# DRAM bytes of that launch at batch 16 from `ncu --set full` (profiles/r01d_ncu_full_tc_kernels.md): read + write
+# DRAM bytes of that launch at batch 16 from `ncu --set full` (profiles/r01e_ncu_full_tc_kernels.md): read + write
 PROBE_DRAM_BYTES_B16 = 403.2e6 + 751.5e6
 
 
