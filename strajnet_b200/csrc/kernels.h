@@ -114,6 +114,13 @@ void layernorm(Ctx& c, const void* x, void* y, int rows, int C, const float* g, 
 void layernorm_gather(Ctx& c, const void* x, void* y, int rows, int C, const float* g, const float* b, float eps,
                       const int* map, int map_len);
 
+// bf16 fast paths for C in {96, 192, 384} (norm_fast.cu); each returns false when the shape is not covered
+bool ln_fast(Ctx& c, bool stats_only, const void* x, void* y, int rows, int C, int ld, const float* g, const float* b,
+             float eps, const void* res, int g_div, int g_mod, const int* map, int map_len, float* mean, float* rstd);
+bool ln_stats_merge_fast(Ctx& c, const void* x, int B, int H, int W, int C, float eps, float* mean, float* rstd);
+bool pe_combine_fast(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, const SjNorm& n0, const SjNorm& n1,
+                     const SjNorm& nf, void* y, float* st_mean, float* st_rstd);
+
 // ---- attention cores (attention.cu) -----------------------------------------------------------
 // Window attention core, modules.py:109-131.  qkv [nWinTotal*64, 3C] (q|k|v, head-major inside),
 // out [nWinTotal*64, C].  mask_mode 0: none; 1: shifted-window mask computed from (H,W,ws,shift);

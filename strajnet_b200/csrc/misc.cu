@@ -607,6 +607,8 @@ void im2col4(Ctx& c, const void* img, int itype, int B, int S, int Cin, int es, 
 void pe_combine(Ctx& c, const void* c0, const void* c1, int B, int P, int pad1, const SjNorm& n0, const SjNorm& n1,
                 const SjNorm& nf, void* y, float* st_mean, float* st_rstd) {
   if (!c.ok() || c.dry) return;
+  static const bool fast_off = getenv("SJ_DISABLE_NORM_FAST") != nullptr;
+  if (!fast_off && pe_combine_fast(c, c0, c1, B, P, pad1, n0, n1, nf, y, st_mean, st_rstd)) return;
   const long long ntok = (long long)B * P * P;
   SJ_LAUNCH(c, "pe_combine", pe_combine_kernel, cdiv(ntok, 8), 256, 0, (const bf16*)c0, (const bf16*)c1, B, P, pad1, n0, n1,
             nf, (bf16*)y, st_mean, st_rstd);

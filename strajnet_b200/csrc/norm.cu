@@ -1,4 +1,6 @@
 // LayerNormalization kernels (Keras semantics: last axis, biased variance).  One warp per row.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sj {
@@ -109,9 +111,15 @@ __global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, int
 
 }  // namespace
 
+static bool norm_fast_disabled() {
+  static const bool off = getenv("SJ_DISABLE_NORM_FAST") != nullptr;
+  return off;
+}
+
 void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* mean, float* rstd) {
   if (!c.ok() || c.dry) return;
   if (C % 4 || ld % 4) { c.fail(SJ_EINVAL); return; }
+  if (!norm_fast_disabled() && ln_fast(c, true, x, nullptr, rows, C, ld, nullptr, nullptr, eps, nullptr, 1, 1, nullptr, 0, mean, rstd)) return;
   int grid = cdiv(rows, 8);
   if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "ln_stats", ln_stats_kernel<bf16>, grid, 256, 0, (const bf16*)x, rows, C, ld, eps, mean, rstd);
   else SJ_LAUNCH(c, "ln_stats", ln_stats_kernel<float>, grid, 256, 0, (const float*)x, rows, C, ld, eps, mean, rstd);
@@ -120,6 +128,7 @@ void ln_stats(Ctx& c, const void* x, int rows, int C, int ld, float eps, float* 
 void ln_stats_merge(Ctx& c, const void* x, int B, int H, int W, int C, float eps, float* mean, float* rstd) {
   if (!c.ok() || c.dry) return;
   if (C % 4) { c.fail(SJ_EINVAL); return; }
+  if (!norm_fast_disabled() && ln_stats_merge_fast(c, x, B, H, W, C, eps, mean, rstd)) return;
   int rows = B * (H / 2) * (W / 2);
   int grid = cdiv(rows, 8);
   if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "ln_stats_merge", ln_stats_merge_kernel<bf16>, grid, 256, 0, (const bf16*)x, B, H, W, C, eps, mean, rstd);
@@ -132,6 +141,7 @@ void layernorm(Ctx& c, const void* x, void* y, int rows, int C, const float* g, 
   if (C % 4) { c.fail(SJ_EINVAL); return; }
   if (g_div <= 0) g_div = 1;
   if (g_mod <= 0) g_mod = 1;
+  if (!norm_fast_disabled() && ln_fast(c, false, x, y, rows, C, C, g, b, eps, res, g_div, g_mod, nullptr, 0, nullptr, nullptr)) return;
   int grid = cdiv(rows, 8);
   if (c.dtype == SJ_BF16)
     SJ_LAUNCH(c, "layernorm", layernorm_kernel<bf16>, grid, 256, 0, (const bf16*)x, (bf16*)y, rows, C, g, b, eps, (const bf16*)res, g_div, g_mod, (const int*)nullptr, 0);
@@ -143,6 +153,7 @@ void layernorm_gather(Ctx& c, const void* x, void* y, int rows, int C, const flo
                       const int* map, int map_len) {
   if (!c.ok() || c.dry) return;
   if (C % 4 || !map || map_len <= 0) { c.fail(SJ_EINVAL); return; }
+  if (!norm_fast_disabled() && ln_fast(c, false, x, y, rows, C, C, g, b, eps, nullptr, 1, 1, map, map_len, nullptr, nullptr)) return;
   int grid = cdiv(rows, 8);
   if (c.dtype == SJ_BF16)
     SJ_LAUNCH(c, "layernorm_gather", layernorm_kernel<bf16>, grid, 256, 0, (const bf16*)x, (bf16*)y, rows, C, g, b, eps, (const bf16*)nullptr, 1, 1, map, map_len);
