@@ -212,6 +212,60 @@ __global__ void im2col4_kernel(const void* __restrict__ img, int itype, int B, i
   *reinterpret_cast<uint4*>(A + tok * Kpad + k0) = u;
 }
 
+// Staged variant: one block = 64 consecutive tokens of one token row.  The four source image rows of those tokens are
+// contiguous spans: they are read with 16-byte loads (fully coalesced), converted, and the kept elements (channel
+// element stride es: plane 0 of the [..., 11, 2] occupancy raster) parked in shared memory as bf16; the A rows are then
+// written with 16-byte stores.  The gather kernel above reads 8 scattered scalars per thread instead.
+constexpr int IM2COL_TOK = 64;
+template <int ITYPE>
+__global__ void __launch_bounds__(256) im2col4_staged_kernel(const void* __restrict__ img, int B, int S, int Cin, int es,
+                                                             int Kpad, bf16* __restrict__ A) {
+  extern __shared__ __align__(16) bf16 im2col_sm[];  // [4 ky][IM2COL_TOK * 4 * Cin]
+  const int P = S / 4, blocks_per_row = P / IM2COL_TOK;
+  const int pj0 = (blockIdx.x % blocks_per_row) * IM2COL_TOK, pi = (blockIdx.x / blocks_per_row) % P;
+  const long long b = blockIdx.x / ((long long)blocks_per_row * P);
+  const int keep_row = IM2COL_TOK * 4 * Cin;      // kept elements per image row
+  const int span = keep_row * es;                 // source elements per image row
+  constexpr int EPV = ITYPE == IN_F32 ? 4 : 16;   // source elements per 16-byte load
+  for (int ky = 0; ky < 4; ++ky) {
+    const long long base = (((b * S + 4 * pi + ky) * S) + 4 * pj0) * (long long)Cin * es;
+    for (int v = threadIdx.x; v < span / EPV; v += 256) {
+      const int e0 = v * EPV;
+      if (ITYPE == IN_F32) {
+        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(img) + base + e0);
+        const float vals[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((e0 + i) % es == 0) im2col_sm[ky * keep_row + (e0 + i) / es] = __float2bfloat16_rn(vals[i]);
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(img) + base + e0);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if ((e0 + i) % es == 0) {
+            const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
+            const float x = ITYPE == IN_U8 ? (byte != 0 ? 1.0f : 0.0f) : (float)(int8_t)byte / 256.0f;
+            im2col_sm[ky * keep_row + (e0 + i) / es] = __float2bfloat16_rn(x);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int k8n = Kpad / 8, K = 16 * Cin, kpr = 4 * Cin;  // kpr: k values per image row of a token
+  for (int i = threadIdx.x; i < IM2COL_TOK * k8n; i += 256) {
+    const int tokl = i / k8n, k0 = (i % k8n) * 8;
+    __align__(16) bf16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      o[j] = k < K ? im2col_sm[(k / kpr) * keep_row + tokl * kpr + k % kpr] : __float2bfloat16_rn(0.f);
+    }
+    const long long tok = (b * P + pi) * P + pj0 + tokl;
+    *reinterpret_cast<uint4*>(A + tok * Kpad + k0) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // y[token] = LN_f( LN_0(c0[token]) + LN_1(c1[token']) ) over E = 96 channels, eps 1e-5 (modules.py:445, :580-587, :602);
 // c1 is optional and may cover only the centre P1 x P1 tokens of the P x P grid (pad1 = (P - P1)/2), contributing 0
 // elsewhere.  One warp per token, 3 channels per lane.
@@ -601,6 +655,18 @@ void patch_embed(Ctx& c, const PatchEmbedP& p) {
 void im2col4(Ctx& c, const void* img, int itype, int B, int S, int Cin, int es, int Kpad, void* A) {
   if (!c.ok() || c.dry) return;
   if (Kpad % 8 || Kpad < 16 * Cin) { c.fail(SJ_EINVAL); return; }
+  static const bool staged_off = getenv("SJ_DISABLE_IM2COL_STAGED") != nullptr;
+  const int P = S / 4, epv = itype == IN_F32 ? 4 : 16;
+  const size_t esz = itype == IN_F32 ? 4 : 1;
+  if (!staged_off && P % IM2COL_TOK == 0 && (IM2COL_TOK * 4 * Cin * es) % epv == 0 && ((size_t)S * Cin * es * esz) % 16 == 0 &&
+      (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+    const size_t smem = (size_t)4 * IM2COL_TOK * 4 * Cin * 2;
+    const int grid = B * P * (P / IM2COL_TOK);
+    if (itype == IN_F32) SJ_LAUNCH(c, "im2col4_staged", im2col4_staged_kernel<IN_F32>, grid, 256, smem, img, B, S, Cin, es, Kpad, (bf16*)A);
+    else if (itype == IN_U8) SJ_LAUNCH(c, "im2col4_staged", im2col4_staged_kernel<IN_U8>, grid, 256, smem, img, B, S, Cin, es, Kpad, (bf16*)A);
+    else SJ_LAUNCH(c, "im2col4_staged", im2col4_staged_kernel<IN_I8_DIV256>, grid, 256, smem, img, B, S, Cin, es, Kpad, (bf16*)A);
+    return;
+  }
   const long long n = (long long)B * (S / 4) * (S / 4) * (Kpad / 8);
   SJ_LAUNCH(c, "im2col4", im2col4_kernel, cdiv(n, 256), 256, 0, img, itype, B, S, Cin, es, Kpad, (bf16*)A);
 }
