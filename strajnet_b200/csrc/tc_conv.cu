@@ -84,7 +84,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   float* bias_s = reinterpret_cast<float*>(bars + 48);  // [Cout] (<= 256 floats), 16-byte aligned
   for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) bias_s[i] = p.bias[i];
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
@@ -160,10 +160,10 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp == 1 || warp == 10) {
-    // Two MMA-issuing warps, one per column phase px (independent TMEM accumulators).  The single issuing thread
-    // spends ~20 scalar instructions per tcgen05.mma, which at N = 48..96 costs more than the MMA itself; two
-    // issuers halve that serial chain.  Each commits to the same mbarriers (arrival count 2).
-    if (lane == 0) {
+    // Two MMA-issuing warps, one per column phase px (independent TMEM accumulators).  Each warp runs its loop
+    // uniformly (descriptors stay in uniform registers) and one elected lane issues; both commit to the same
+    // mbarriers (arrival count 2).
+    {
       const int px = warp == 1 ? 0 : 1;
       const uint32_t idesc = make_idesc_bf16(BM, p.Cout);
       constexpr uint32_t A_HI = desc_hi(AROWB, PW * AROWB), B_HI = desc_hi(ROWB, 8 * ROWB);
@@ -199,33 +199,39 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               // column tap dx = dxi-1 feeds phase px iff b = dxi - px is 0 or 1; in a streamed stage the tile of px1 is
               // slot 1 only for the shared centre tap
               const int b = dxi - px;
-              if (b == 0 || b == 1) {
-                const int sl = (dxi == 1 && px == 1) ? 1 : 0;
+              if (elect_one()) {
+                if (b == 0 || b == 1) {
+                  const int sl = (dxi == 1 && px == 1) ? 1 : 0;
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                  // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
-                  const uint32_t view = a_lo + (((a * PW + dxi) * AROWB) >> 4);
-                  const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
-                                           : bstage_lo + (uint32_t)(sl * NCH + ch) * b_sub16;
+                  for (int ch = 0; ch < NCH; ++ch) {
+                    // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
+                    const uint32_t view = a_lo + (((a * PW + dxi) * AROWB) >> 4);
+                    const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
+                                             : bstage_lo + (uint32_t)(sl * NCH + ch) * b_sub16;
 #pragma unroll
-                  for (int k = 0; k < KC / 16; ++k) {
-                    const int kk = ch * (KC / 16) + k;  // K step (16 channels) within the slot
-                    const uint32_t va = view + (kk / (AKC / 16)) * A_SUB16 + 2 * (kk % (AKC / 16));
-                    umma_bf16_w(d_tmem, va, A_HI, vb + 2 * k, B_HI, idesc, started);
-                    started = 1;
+                    for (int k = 0; k < KC / 16; ++k) {
+                      const int kk = ch * (KC / 16) + k;  // K step (16 channels) within the slot
+                      const uint32_t va = view + (kk / (AKC / 16)) * A_SUB16 + 2 * (kk % (AKC / 16));
+                      umma_bf16_w(d_tmem, va, A_HI, vb + 2 * k, B_HI, idesc, started);
+                      started = 1;
+                    }
                   }
                 }
+                if (!RESB) umma_commit(&bempty[bs_]);
               }
+              __syncwarp();
+              if (b == 0 || b == 1) started = 1;
               if (!RESB) {
-                umma_commit(&bempty[bs_]);
                 if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
               }
             }
           }
-          umma_commit(&aempty[as_]);
+          if (elect_one()) umma_commit(&aempty[as_]);
+          __syncwarp();
           if (++as_ == p.na) { as_ = 0; aph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (++acc == p.nacc) { acc = 0; tph ^= 1; }
       }
     }

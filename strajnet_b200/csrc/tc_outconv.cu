@@ -52,7 +52,7 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
   uint64_t* zempty = zfull + NZ;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zempty + NZ);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapO);
     prefetch_tmap(&mapF);
@@ -93,22 +93,23 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 32);
-      constexpr uint32_t HI = desc_hi(128, 1024);
-      const uint32_t w_lo = desc_lo(smem_u32(smem + OFF_W));
-      int slot = 0, zb = 0;
-      uint32_t ph = 0, zph = 0;
-      mbar_wait(wfull, 0);
-      tc_fence_after();
-      for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+    // uniform loop over the whole warp (descriptors in uniform registers); one elected lane issues
+    const uint32_t idesc = make_idesc_bf16(128, 32);
+    constexpr uint32_t HI = desc_hi(128, 1024);
+    const uint32_t w_lo = desc_lo(smem_u32(smem + OFF_W));
+    int slot = 0, zb = 0;
+    uint32_t ph = 0, zph = 0;
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
 #pragma unroll 1
-        for (int th = 0; th < 16; ++th) {
-          mbar_wait(&afull[slot], ph);
-          mbar_wait(&zempty[zb], zph ^ 1);
-          tc_fence_after();
-          const uint32_t a_lo = desc_lo(smem_u32(smem + slot * A_SLOT));
-          const uint32_t wh = w_lo + (uint32_t)((th & 1) * (W_HEAD >> 4));
+      for (int th = 0; th < 16; ++th) {
+        mbar_wait(&afull[slot], ph);
+        mbar_wait(&zempty[zb], zph ^ 1);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smem_u32(smem + slot * A_SLOT));
+        const uint32_t wh = w_lo + (uint32_t)((th & 1) * (W_HEAD >> 4));
+        if (elect_one()) {
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
@@ -117,9 +118,10 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
                           k != 0);
           umma_commit(&aempty[slot]);
           umma_commit(&zfull[zb]);
-          if (++slot == NA) { slot = 0; ph ^= 1; }
-          if (++zb == NZ) { zb = 0; zph ^= 1; }
         }
+        __syncwarp();
+        if (++slot == NA) { slot = 0; ph ^= 1; }
+        if (++zb == NZ) { zb = 0; zph ^= 1; }
       }
     }
   } else {
