@@ -392,3 +392,34 @@ def test_strajnet_tf_checkpoint_roundtrip(sj, tmp_path):
     m2.load_weights(prefix)
     inp = O.make_inputs(1, 256, seed=41)
     assert torch.equal(_fwd(m, inp), _fwd(m2, inp))
+
+
+def test_forward_into_cuda_graph_replay(sj):
+    """forward_into(graph=True): first use launches + captures, later uses replay; results equal the plain launches
+    bit for bit, also after the inputs were overwritten in place and after set_weights invalidated the capture."""
+    m = _model(sj, dtype="bfloat16")
+    dev = m.device
+    inp = {k: v.to(dev) for k, v in O.make_inputs(2, 256, seed=51).items()}
+    out = torch.empty(2, 256, 256, 32, device=dev)
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        args = (inp["ogm"], inp["map_img"], inp["obs"], inp["occ"], inp["flow"])
+        ref = m.forward_into(torch.empty_like(out), *args).clone()
+        for _ in range(3):  # capture, replay, replay
+            out.zero_()
+            m.forward_into(out, *args, graph=True)
+            assert torch.equal(out, ref)
+        assert len(m._graphs) == 1
+        new = {k: v.to(dev) for k, v in O.make_inputs(2, 256, seed=52).items()}
+        for k in inp:
+            inp[k].copy_(new[k])  # same buffers, new contents
+        ref2 = m.forward_into(torch.empty_like(out), *args).clone()
+        m.forward_into(out, *args, graph=True)
+        assert torch.equal(out, ref2) and not torch.equal(ref, ref2)
+        m.set_weights(O.make_weights(O.CFG256, seed=1))
+        assert len(m._graphs) == 0
+        ref3 = m.forward_into(torch.empty_like(out), *args).clone()
+        m.forward_into(out, *args, graph=True)
+        m.forward_into(out, *args, graph=True)
+        assert torch.equal(out, ref3)
+    s.synchronize()
