@@ -603,6 +603,7 @@ class STrajNet(Layer):
             raise ValueError("STrajNet: input_size 512 needs large_ogm=True and 256 needs large_ogm=False (SURVEY Q13)")
         self.fg_msa, self.fg, self.large_ogm = fg_msa, fg, large_ogm
         self._graphs = {}
+        self._graph_failed = False
 
     def weight_shapes(self):
         return W.model_shapes(self.cfg, self.fg_msa, self.fg)
@@ -625,7 +626,7 @@ class STrajNet(Layer):
         graph=True: for callers that reuse the SAME buffers every step (serving slots): the ~90 launches of the forward
         are captured into a CUDA graph on first use of this set of buffers and replayed afterwards (launch gaps are
         ~6 % of the batch-16 step).  Not for one-off calls: every new set of pointers is a new capture."""
-        if not graph or torch.cuda.is_current_stream_capturing():
+        if not graph or self._graph_failed or torch.cuda.is_current_stream_capturing():
             return self._launch(out, ogm, map_img, obs, occ, flow)
         self.packed()
         key = (out.data_ptr(), ogm.data_ptr(), map_img.data_ptr(), obs.data_ptr(), occ.data_ptr(), flow.data_ptr(),
@@ -639,8 +640,15 @@ class STrajNet(Layer):
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
-            self._launch(out, ogm, map_img, obs, occ, flow)
+        try:
+            with torch.cuda.graph(g, stream=side):
+                self._launch(out, ogm, map_img, obs, occ, flow)
+        except RuntimeError as e:  # capture refused (driver / context state): keep serving with plain launches
+            import warnings
+            warnings.warn(f"STrajNet: CUDA graph capture failed, falling back to stream launches: {e}")
+            self._graph_failed = True
+            cur.wait_stream(side)
+            return out
         cur.wait_stream(side)
         if len(self._graphs) >= 8:  # bounded: serving uses a handful of slots
             self._graphs.pop(next(iter(self._graphs)))
