@@ -158,6 +158,13 @@ const char* sj_last_cuda_error(void); /* text of the last CUDA failure seen by t
 long long sj_launch_count(int reset);
 /* of which tcgen05 (tensor-core) kernels */
 long long sj_tc_launch_count(int reset);
+/* Programmatic dependent launch (CUDA launch attribute "programmatic stream serialization"): when on (the default;
+ * SJ_NO_PDL=1 in the environment turns it off), each kernel of a forward is launched so that its prologue overlaps
+ * the tail of its predecessor on the stream; every kernel of the library orders itself behind its predecessor with
+ * griddepcontrol.wait before touching activations, so results are identical either way.  `mask`: bit 0 = the
+ * tcgen05 kernels, bit 1 = all other kernels (3 = every launch, 0 = off; SJ_PDL_MASK in the environment sets the
+ * initial value).  Process-wide; returns the previous mask.  mask < 0 only queries. */
+int sj_set_pdl(int mask);
 
 /* Host-side helper of the record / checkpoint readers (scope rows f2, f3): CRC-32C (Castagnoli) of `n` bytes,
  * continuing from `crc` (0 to start).  This is the checksum of the TFRecord framing the reference reads through

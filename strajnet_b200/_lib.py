@@ -90,6 +90,7 @@ SIGNATURES = {
     "sj_last_cuda_error": (C.c_char_p, []),
     "sj_launch_count": (_ll, [_i]),
     "sj_tc_launch_count": (_ll, [_i]),
+    "sj_set_pdl": (_i, [_i]),
     "sj_crc32c": (C.c_uint32, [_p, _sz, C.c_uint32]),
     "sj_probe_start": (_i, [C.c_char_p]),
     "sj_probe_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),

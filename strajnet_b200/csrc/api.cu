@@ -13,6 +13,15 @@ TlsState& tls() {
   return s;
 }
 
+static int g_pdl = -1;  // -1: not decided yet (environment); else bit 0 = tcgen05 kernels, bit 1 = the others
+int pdl_mask() {
+  if (g_pdl < 0) {
+    const char* m = getenv("SJ_PDL_MASK");
+    g_pdl = getenv("SJ_NO_PDL") ? 0 : (m ? atoi(m) & 3 : 0);
+  }
+  return g_pdl;
+}
+
 void note_launch(Ctx& c, const char* what) {
   tls().launches++;
   if (what[0] == 't' && what[1] == 'c' && what[2] == '_') tls().tc_launches++;
@@ -713,6 +722,11 @@ long long sj_launch_count(int reset) {
   return n;
 }
 
+int sj_set_pdl(int on) {
+  const int prev = sj::pdl_mask();
+  if (on >= 0) sj::g_pdl = on & 3;
+  return prev;
+}
 long long sj_tc_launch_count(int reset) {
   long long n = tls().tc_launches;
   if (reset) tls().tc_launches = 0;

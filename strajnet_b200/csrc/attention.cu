@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(64) window_attn_kernel(const T* __restrict__ q
                                                          const float* __restrict__ table, int C, int heads,
                                                          int mask_mode, int H, int W, int shift,
                                                          const float* __restrict__ mask, int nW) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int DS = D + 4;
   __shared__ __align__(16) float Ks[64][DS];
   __shared__ __align__(16) float Vs[64][DS];
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(64) window_attn_kernel(const T* __restrict__ q
 // ------------------------------------------------------------------------------------------------
 template <typename T, int D, bool FG>
 __global__ void mha_kernel(const MhaP p) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int DP = (D + 3) & ~3;
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;                    // [Nk][DP]

@@ -46,6 +46,8 @@ struct AttnP {
 // DP: head dim padded to a multiple of 16; KCH: keys per inner chunk (16 or 64)
 template <int DP, int KCH, int MODE>
 __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnP p) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int RS = DP + 8;  // smem row stride in elements: 16-byte aligned rows, conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Ks = reinterpret_cast<bf16*>(smem_raw);               // [hpb][nk_pad][RS]

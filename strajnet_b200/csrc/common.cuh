@@ -73,14 +73,41 @@ void note_launch(Ctx& c, const char* what);
 int probe_before(Ctx& c);
 void probe_after(Ctx& c, int slot);
 
-#define SJ_LAUNCH(ctx, what, kernel, grid, block, smem, ...)                 \
-  do {                                                                      \
-    if (!(ctx).dry && (ctx).ok()) {                                         \
-      int sj_slot_ = sj::probe_before(ctx);                                 \
-      kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);       \
-      sj::probe_after((ctx), sj_slot_);                                     \
-      sj::note_launch((ctx), what);                                         \
-    }                                                                       \
+// Programmatic dependent launch (PDL): every kernel of the library executes pdl_wait() before its first access to
+// memory another kernel of the forward may have written (and before its first global write), and pdl_trigger() near
+// its top.  Launched with programmatic stream serialisation, kernel i+1 then gets its CTAs scheduled, barriers
+// initialised, TMEM allocated and constant weights staged while kernel i drains, instead of after its last CTA has
+// retired.  Both are no-ops for a kernel launched without the attribute (SJ_NO_PDL=1).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// which launches get the attribute: bit 0 = tcgen05 kernels ("tc_*"), bit 1 = all others
+int pdl_mask();
+
+template <typename... Exp, typename... Act>
+inline void launch_kernel(const char* what, cudaStream_t stream, dim3 grid, dim3 block, size_t smem,
+                          void (*kernel)(Exp...), Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const bool is_tc = what[0] == 't' && what[1] == 'c' && what[2] == '_';
+  cfg.numAttrs = (pdl_mask() & (is_tc ? 1 : 2)) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);
+}
+
+#define SJ_LAUNCH(ctx, what, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                        \
+    if (!(ctx).dry && (ctx).ok()) {                                                           \
+      int sj_slot_ = sj::probe_before(ctx);                                                   \
+      sj::launch_kernel(what, (ctx).stream, dim3(grid), dim3(block), (smem), kernel, __VA_ARGS__);  \
+      sj::probe_after((ctx), sj_slot_);                                                       \
+      sj::note_launch((ctx), what);                                                           \
+    }                                                                                         \
   } while (0)
 
 // ---- typed element access --------------------------------------------------------------------

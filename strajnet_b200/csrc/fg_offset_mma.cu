@@ -16,6 +16,8 @@ constexpr int HALO_PIX = 4 * 18;
 
 __global__ void __launch_bounds__(256) fg_offset_mma_kernel(const bf16* __restrict__ q, int ldq, SjFgmsaW w,
                                                             float* __restrict__ off, float* __restrict__ pos) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* qs = reinterpret_cast<bf16*>(smem_raw);                       // [4][18][PS]
   float* red = reinterpret_cast<float*>(qs + HALO_PIX * PS);          // [8 warps][32 pixels]

@@ -22,6 +22,8 @@ __device__ __forceinline__ long long map_row(const RowMap& r, int m, int g) {
 
 template <typename T, int AMODE, int BN>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmP p) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int TN = BN / 16;  // columns per thread (8 or 4)
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];

@@ -9,6 +9,8 @@ namespace {
 
 // ---------------------------------------------------------------- integer maps (bit-exact rows)
 __global__ void rel_pos_index_kernel(int ws, int64_t* out) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int N = ws * ws;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * N) return;
@@ -17,6 +19,8 @@ __global__ void rel_pos_index_kernel(int ws, int64_t* out) {
 }
 
 __global__ void shift_mask_kernel(int H, int W, int ws, int shift, float* out) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int N = ws * ws;
   long long total = (long long)(H / ws) * (W / ws) * N * N;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,6 +33,8 @@ __global__ void shift_mask_kernel(int H, int W, int ws, int shift, float* out) {
 }
 
 __global__ void window_token_map_kernel(int H, int W, int ws, int shift, int32_t* out) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int N = ws * ws;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
@@ -42,6 +48,8 @@ __global__ void window_token_map_kernel(int H, int W, int ws, int shift, int32_t
 template <typename T>
 __global__ void window_permute_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C, int H, int W,
                                       int ws, int scatter) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int c4 = C / 4;
   if (i >= rows * c4) return;
@@ -58,6 +66,8 @@ __global__ void window_permute_kernel(const T* __restrict__ x, T* __restrict__ y
 
 template <typename T>
 __global__ void center_crop_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int P, int C) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int h = P / 2, o = P / 4, c4 = C / 4;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * h * h * c4) return;
@@ -73,6 +83,8 @@ constexpr int PE_KMAX = 16 * 11;
 
 template <typename T>
 __global__ void patch_embed_kernel(const PatchEmbedP p) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   __shared__ __align__(16) float ins[PE_TOK][PE_KMAX];
   __shared__ float vals[PE_TOK][128];
   __shared__ float stat[PE_TOK][2];
@@ -186,6 +198,8 @@ __global__ void patch_embed_kernel(const PatchEmbedP p) {
 // so the conv becomes a plain tcgen05 GEMM.  One thread per 8 consecutive k (one 16-byte store).
 __global__ void im2col4_kernel(const void* __restrict__ img, int itype, int B, int S, int Cin, int es, int Kpad,
                                bf16* __restrict__ A) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int k8n = Kpad / 8, P = S / 4, K = 16 * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * P * P * k8n) return;
@@ -220,6 +234,8 @@ constexpr int IM2COL_TOK = 64;
 template <int ITYPE>
 __global__ void __launch_bounds__(256) im2col4_staged_kernel(const void* __restrict__ img, int B, int S, int Cin, int es,
                                                              int Kpad, bf16* __restrict__ A) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) bf16 im2col_sm[];  // [4 ky][IM2COL_TOK * 4 * Cin]
   const int P = S / 4, blocks_per_row = P / IM2COL_TOK;
   const int pj0 = (blockIdx.x % blocks_per_row) * IM2COL_TOK, pi = (blockIdx.x / blocks_per_row) % P;
@@ -272,6 +288,8 @@ __global__ void __launch_bounds__(256) im2col4_staged_kernel(const void* __restr
 __global__ void pe_combine_kernel(const bf16* __restrict__ c0, const bf16* __restrict__ c1, int B, int P, int pad1,
                                   SjNorm n0, SjNorm n1, SjNorm nf, bf16* __restrict__ y, float* __restrict__ st_mean,
                                   float* __restrict__ st_rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const long long tok = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (tok >= (long long)B * P * P) return;
@@ -323,6 +341,8 @@ constexpr int FGP = 8;
 template <typename T>
 __global__ void __launch_bounds__(384) fg_offset_kernel(const T* __restrict__ q, int ldq, SjFgmsaW w,
                                                         float* __restrict__ off, float* __restrict__ pos) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   __shared__ __align__(16) float qs[3][FGP + 2][384];
   float (*us)[384] = reinterpret_cast<float (*)[384]>(&qs[0][0][0]);  // aliases qs: dead after the conv
   __shared__ float red[12][FGP];
@@ -398,6 +418,8 @@ __global__ void __launch_bounds__(384) fg_offset_kernel(const T* __restrict__ q,
 template <typename T>
 __global__ void build_query_kernel(const T* __restrict__ q2, const float* __restrict__ off, const float* __restrict__ w2,
                                    const float* __restrict__ b2, int B, int fg, T* __restrict__ query) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*8*256*96 float4 groups
   if (i >= (long long)B * 8 * 256 * 96) return;
   int c = (i % 96) * 4;
@@ -424,6 +446,8 @@ template <typename T>
 __global__ void traj_node_kernel(const float* __restrict__ obs, const float* __restrict__ occ, SjTrajW w, int B,
                                  T* __restrict__ node, int* __restrict__ stepmask, int* __restrict__ cmask,
                                  float* __restrict__ vec) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   __shared__ float X[88];
   const int a = blockIdx.x, b = a / 64, i = a % 64, n = threadIdx.x;
   const float* src = i < 48 ? obs + ((long long)b * 48 + i) * 88 : occ + ((long long)b * 16 + (i - 48)) * 88;
@@ -453,6 +477,8 @@ __global__ void traj_node_kernel(const float* __restrict__ obs, const float* __r
 
 template <typename T>
 __global__ void traj_pool_concat_kernel(const T* __restrict__ proj, const float* __restrict__ vec, T* __restrict__ cat) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int a = blockIdx.x, n = threadIdx.x;  // 384 threads
   float v;
   if (n < 320) {
@@ -467,6 +493,8 @@ __global__ void traj_pool_concat_kernel(const T* __restrict__ proj, const float*
 template <typename T>
 __global__ void traj_prep_kernel(const T* __restrict__ E, const int* __restrict__ cmask, const float* __restrict__ seg_w,
                                  T* __restrict__ A, T* __restrict__ Q) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int a = blockIdx.x, n = threadIdx.x;  // 384 threads
   float e = ldf<T>(E + (long long)a * 384 + n) * (float)cmask[a];
   float s = seg_w[((a % 64) < 48 ? 0 : 384) + n];
@@ -478,6 +506,8 @@ __global__ void traj_prep_kernel(const T* __restrict__ E, const int* __restrict_
 template <typename T>
 __global__ void traj_final_kernel(const T* __restrict__ E, const T* __restrict__ F2, SjTrajW w, int n_actors,
                                   T* __restrict__ key) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int a = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
   if (a >= n_actors) return;
   float f[12], s = 0.f;
@@ -525,6 +555,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) out_conv_kernel(const T* __restrict__ xo, const T* __restrict__ xf,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        int out_layout, void* __restrict__ outv) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t oc_smem[];
   T* tile = reinterpret_cast<T*>(oc_smem);                                                       // [18][34][56]
   float2* ws = reinterpret_cast<float2*>(oc_smem + (OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * sizeof(T));  // [2][432]

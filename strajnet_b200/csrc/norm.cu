@@ -9,6 +9,8 @@ namespace {
 template <typename T>
 __global__ void ln_stats_kernel(const T* __restrict__ x, int rows, int C, int ld, float eps, float* __restrict__ mean,
                                 float* __restrict__ rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -36,6 +38,8 @@ __global__ void ln_stats_kernel(const T* __restrict__ x, int rows, int C, int ld
 template <typename T>
 __global__ void ln_stats_merge_kernel(const T* __restrict__ x, int B, int H, int W, int C, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   int ho = H / 2, wo = W / 2;
@@ -71,6 +75,8 @@ template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, const float* __restrict__ g,
                                  const float* __restrict__ b, float eps, const T* __restrict__ res, int g_div, int g_mod,
                                  const int* __restrict__ map, int map_len) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;

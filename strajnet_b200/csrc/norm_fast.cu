@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const bf16* __restrict__ x
                                                       const bf16* __restrict__ res, int g_div, int g_mod,
                                                       const int* __restrict__ map, int map_len, float* __restrict__ mean,
                                                       float* __restrict__ rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int C = 24 * LPR, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const bf16* __restrict__ x
 template <int LPS>
 __global__ void __launch_bounds__(256) ln_stats_merge_fast_kernel(const bf16* __restrict__ x, int B, int H, int W, float eps,
                                                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int C = 24 * LPS, LPR = 4 * LPS, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, q = sub / LPS, part = sub % LPS;
   const int ho = H / 2, wo = W / 2, rows = B * ho * wo;
@@ -120,6 +124,8 @@ __global__ void __launch_bounds__(256) pe_combine_fast_kernel(const bf16* __rest
                                                               int P, int pad1, SjNorm n0, SjNorm n1, SjNorm nf,
                                                               bf16* __restrict__ y, float* __restrict__ st_mean,
                                                               float* __restrict__ st_rstd) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   const int lane = threadIdx.x & 31, sub = lane & 3;
   const long long ntok = (long long)B * P * P;
   const long long tok = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + (lane >> 2);

@@ -105,6 +105,10 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp != 0) {  // the producer lane waits after it has issued the (constant) resident weights
+    pdl_wait();
+    pdl_trigger();
+  }
 
   const int groups = p.Cin / (KC * NCH);       // A slots consumed per item
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -125,6 +129,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 tma_load_2d(smem_b + (((a * NCH + ch) * 4) + px * 2 + b) * b_sub, &mapB, &bfull[0],
                             (a * 2 + b) * p.Cin + ch * KC, (py * 2 + px) * p.Cout);
       }
+      pdl_wait();
       int as_ = 0, bs_ = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {

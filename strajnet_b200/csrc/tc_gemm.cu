@@ -11,6 +11,7 @@
 // LayerNorm fold: LN(x).W + b == rstd*(x.(g*W) - mean*colsum(g*W)) + (beta.W + b), so the raw
 // activations go through TMA untouched and the per-row affine is applied in the epilogue.
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.h"
@@ -51,7 +52,10 @@ struct KParams {
 };
 
 // ACT / LN are compile-time so the fully unrolled epilogue stays small enough for the instruction caches
-template <int ACT, bool LN>
+// RPF (residual prefetch): the residual rows of tile i+1 are fetched into registers while tile i is in its epilogue
+// (each 32-column chunk is re-loaded for the next tile right after it has been consumed), so the epilogue never sits
+// on a global-memory round trip.  Needs 32-column chunks only and at most 96 columns per thread.
+template <int ACT, bool LN, bool RPF = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,6 +92,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, tensor-map prefetch) overlaps the previous kernel's tail
+  pdl_trigger();
 
   const int tiles_per_group = p.m_tiles * p.n_tiles;
   const int num_tiles = tiles_per_group * p.groups;
@@ -169,26 +175,63 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int g = tile / tiles_per_group, rem = tile % tiles_per_group;
+    // output row of this thread in a tile: validity, C/R row index (after the row maps), group, first column
+    auto coords = [&](int tile, int& g, int& n0, int& m, bool& valid, long long& crow) {
+      g = tile / tiles_per_group;
+      const int rem = tile % tiles_per_group;
       const int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
-      const int m = mt * BM + quarter * 32 + lane;
-      const int n0 = nt * p.BN;
-      const bool valid = m < p.M;
-      long long crow = 0;
-      float mean = 0.f, rstd = 1.f;
+      m = mt * BM + quarter * 32 + lane;
+      n0 = nt * p.BN;
+      valid = m < p.M;
+      crow = 0;
       if (valid) {
         crow = m;
         if (p.cm.inner > 0) crow = (long long)(m / p.cm.inner) * p.cm.outer + (m % p.cm.inner);
         crow += (long long)g * p.cm.gstride;
         if (p.cm.map) crow = (crow / p.cm.map_len) * p.cm.map_len + p.cm.map[crow % p.cm.map_len];
-        if (LN) {
-          // LN statistics are indexed like the A rows
-          long long arow = m;
-          if (p.a_mode == 1) arow = ((long long)(m / p.a_inner) * p.groups + g) * p.a_inner + (m % p.a_inner);
-          mean = p.ln_mean[arow];
-          rstd = p.ln_rstd[arow];
+      }
+    };
+    constexpr int RCH = 3;  // RPF: at most three 32-column chunks per thread
+    uint4 rn[RPF ? 4 * RCH : 1];
+    auto prefetch = [&](int ci, long long crow_, int n0_) {
+      if constexpr (RPF) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rn[4 * ci + i] = *reinterpret_cast<const uint4*>(p.R + crow_ * p.ldr + n0_ + c_begin + 32 * ci + 8 * i);
+      }
+    };
+    if constexpr (RPF) {
+      if ((int)blockIdx.x < num_tiles) {
+        int g, n0, m;
+        bool valid;
+        long long crow;
+        coords(blockIdx.x, g, n0, m, valid, crow);
+#pragma unroll
+        for (int ci = 0; ci < RCH; ++ci)
+          if (valid && c_begin + 32 * ci < c_end) prefetch(ci, crow, n0);
+      }
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int g, n0, m;
+      bool valid;
+      long long crow;
+      coords(tile, g, n0, m, valid, crow);
+      bool nvalid = false;
+      long long ncrow = 0;
+      int nn0 = 0;
+      if constexpr (RPF) {
+        if (tile + (int)gridDim.x < num_tiles) {
+          int ng, nm;
+          coords(tile + gridDim.x, ng, nn0, nm, nvalid, ncrow);
         }
+      }
+      float mean = 0.f, rstd = 1.f;
+      if (valid && LN) {
+        // LN statistics are indexed like the A rows
+        long long arow = m;
+        if (p.a_mode == 1) arow = ((long long)(m / p.a_inner) * p.groups + g) * p.a_inner + (m % p.a_inner);
+        mean = p.ln_mean[arow];
+        rstd = p.ln_rstd[arow];
       }
       const float* bias = p.bias ? (p.vec_smem ? vec_s : p.bias) + (long long)g * p.bias_gstride : nullptr;
       const float* lns = LN ? (p.vec_smem ? vec_s + p.vec_smem : p.ln_s) + (long long)g * p.ln_gstride : nullptr;
@@ -198,17 +241,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float st_s = 0.f, st_q = 0.f;  // statistics of this thread's share of the (bf16-rounded) output row
       // residual rows are fetched BEFORE the TMEM load of the same columns so the global-memory latency overlaps
       // the tcgen05.ld round trip; everything is fully unrolled so v[] / rr[] stay in registers
-      auto chunk = [&](auto cnt_tag, int c) {
+      auto chunk = [&](auto cnt_tag, int c, auto ci_tag) {
         constexpr int CNT = decltype(cnt_tag)::value;
+        constexpr int CI = decltype(ci_tag)::value;  // RPF: which chunk of the prefetched residual registers
         const int n = n0 + c;
         float v[CNT];
         uint4 rr[CNT / 8];
-        if (valid && p.R) {
+        if constexpr (!RPF) {
+          if (valid && p.R) {
 #pragma unroll
-          for (int i = 0; i < CNT / 8; ++i) rr[i] = *reinterpret_cast<const uint4*>(p.R + crow * p.ldr + n + 8 * i);
+            for (int i = 0; i < CNT / 8; ++i) rr[i] = *reinterpret_cast<const uint4*>(p.R + crow * p.ldr + n + 8 * i);
+          }
         }
         if constexpr (CNT == 32) tmem_ld32(t_addr + c, v);
         else tmem_ld16(t_addr + c, v);
+        if constexpr (RPF) {
+#pragma unroll
+          for (int i = 0; i < CNT / 8; ++i) rr[i] = rn[4 * CI + i];
+          if (nvalid) prefetch(CI, ncrow, nn0);  // this chunk's registers are free again: fetch the next tile's
+        }
         if (!valid) return;
 #pragma unroll
         for (int i = 0; i < CNT; i += 4) {  // 16-byte loads of the per-column vectors (L1-resident)
@@ -243,9 +294,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           st8_bf16(p.C + crow * p.ldc + n + i, v + i);
         }
       };
-      int c = c_begin;
-      for (; c + 32 <= c_end; c += 32) chunk(std::integral_constant<int, 32>{}, c);
-      if (c < c_end) chunk(std::integral_constant<int, 16>{}, c);
+      if constexpr (RPF) {
+        if (c_begin < c_end) chunk(std::integral_constant<int, 32>{}, c_begin, std::integral_constant<int, 0>{});
+        if (c_begin + 32 < c_end) chunk(std::integral_constant<int, 32>{}, c_begin + 32, std::integral_constant<int, 1>{});
+        if (c_begin + 64 < c_end) chunk(std::integral_constant<int, 32>{}, c_begin + 64, std::integral_constant<int, 2>{});
+      } else {
+        int c = c_begin;
+        for (; c + 32 <= c_end; c += 32) chunk(std::integral_constant<int, 32>{}, c, std::integral_constant<int, 0>{});
+        if (c < c_end) chunk(std::integral_constant<int, 16>{}, c, std::integral_constant<int, 0>{});
+      }
       if (p.st_mean) {
         // the two warps of a TMEM lane quarter each hold half of the row: combine through shared memory
         const int rloc = quarter * 32 + lane;
@@ -411,18 +468,29 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
   const bool ln = a.ln_mean != nullptr;
-#define SJ_TCG(ACT_, LN_)                                                                                             \
+#define SJ_TCG(ACT_, LN_, RPF_)                                                                                       \
   do {                                                                                                                \
-    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=  \
-        cudaSuccess) {                                                                                                \
+    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_, RPF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                             227 * 1024) != cudaSuccess) {                                                            \
       c.fail(SJ_ECUDA);                                                                                               \
       return;                                                                                                         \
     }                                                                                                                 \
-    SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_>), grid, NTHREADS, smem_launch, mapA, mapB, p);                 \
+    SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_, RPF_>), grid, NTHREADS, smem_launch, mapA, mapB, p);           \
   } while (0)
-  if (a.act == ACT_GELU) { if (ln) SJ_TCG(ACT_GELU, true); else SJ_TCG(ACT_GELU, false); }
-  else if (a.act == ACT_ELU) { if (ln) SJ_TCG(ACT_ELU, true); else SJ_TCG(ACT_ELU, false); }
-  else { if (ln) SJ_TCG(ACT_NONE, true); else SJ_TCG(ACT_NONE, false); }
+  // residual prefetch: both column halves of a tile must be whole 32-column chunks, at most three per thread
+  const int csplit = ((p.BN / 16 + 1) / 2) * 16, w0 = csplit, w1 = p.BN - csplit;
+  static const bool rpf_off = getenv("SJ_NO_RPF") != nullptr;
+  const bool rpf = a.R && !ln && !rpf_off && w0 % 32 == 0 && w1 % 32 == 0 && w0 <= 96 && w1 <= 96 && w1 > 0;
+  if (a.act == ACT_GELU) { if (ln) SJ_TCG(ACT_GELU, true, false); else SJ_TCG(ACT_GELU, false, false); }
+  else if (a.act == ACT_ELU) {
+    if (ln) SJ_TCG(ACT_ELU, true, false);
+    else if (rpf) SJ_TCG(ACT_ELU, false, true);
+    else SJ_TCG(ACT_ELU, false, false);
+  } else {
+    if (ln) SJ_TCG(ACT_NONE, true, false);
+    else if (rpf) SJ_TCG(ACT_NONE, false, true);
+    else SJ_TCG(ACT_NONE, false, false);
+  }
 #undef SJ_TCG
 }
 

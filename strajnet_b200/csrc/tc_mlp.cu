@@ -90,6 +90,10 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp != 0) {  // the producer lane waits after it has issued the (constant) resident weights
+    pdl_wait();
+    pdl_trigger();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -98,6 +102,7 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         for (int hf = 0; hf < 2; ++hf)
           tma_load_2d(smem + OFF_W1 + c * W1_CHUNK + hf * 192 * 64, &mapW1, &bar[B_WFULL], c * 32, hf * 192);
       for (int c = 0; c < 12; ++c) tma_load_2d(smem + OFF_W2 + c * W2_CHUNK, &mapW2, &bar[B_WFULL], c * 32, 0);
+      pdl_wait();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);

@@ -74,11 +74,16 @@ tc_outconv_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr int TILES_X = 256 / TW, TILES_PER_IMG = TILES_X * (256 / TH);
+  if (warp != 0) {  // the producer lane waits after it has issued the (constant) resident weights
+    pdl_wait();
+    pdl_trigger();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(wfull, 2 * W_HEAD);
       for (int head = 0; head < 2; ++head) tma_load_2d(smem + OFF_W + head * W_HEAD, &mapW, wfull, 0, head * 32);
+      pdl_wait();
       int slot = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {

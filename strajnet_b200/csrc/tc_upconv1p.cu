@@ -78,6 +78,10 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int phase = blockIdx.x & 3, py = phase >> 1, px = phase & 1;
   const int t_first = blockIdx.x >> 2, t_step = gridDim.x >> 2;
+  if (warp != 0) {  // the producer lane waits after it has issued the (constant) resident weights
+    pdl_wait();
+    pdl_trigger();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -85,6 +89,7 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       for (int ch = 0; ch < NCH; ++ch)
         for (int tap = 0; tap < 4; ++tap)  // tap = a*2 + b
           tma_load_2d(smem_b + (ch * 4 + tap) * B_TILE, &mapB, bfull, tap * CIN + ch * KC, phase * COUT);
+      pdl_wait();
       int as_ = 0;
       uint32_t aph = 0;
       for (int t = t_first; t < p.num_tiles; t += t_step) {

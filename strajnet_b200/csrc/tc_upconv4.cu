@@ -89,6 +89,10 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  if (warp != 0) {  // the producer lane waits after it has issued the (constant) resident weights
+    pdl_wait();
+    pdl_trigger();
+  }
 
   // slot table: 0-3 centre (ring 0..3); 4,5 view (0,1); 6,7 view (1,2); 8,9 view (2,1); 10 view (1,0) ring 0;
   // 11 view (1,0) ring 3; 12..15 corners (0,0) r0, (0,2) r1, (2,2) r2, (2,0) r3
@@ -104,6 +108,7 @@ tc_upconv4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int a = SLOTS[s].ro - py, b = SLOTS[s].dx - px;
           tma_load_2d(smem_b + (ch * 16 + s) * B_TILE, &mapB, bfull, (a * 2 + b) * CIN + ch * KC, (py * 2 + px) * COUT);
         }
+      pdl_wait();
       int as_ = 0;
       uint32_t aph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {

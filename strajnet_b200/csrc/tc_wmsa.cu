@@ -129,6 +129,8 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_a = *tmem_slot, tmem_proj = tmem_a + 128;
+  pdl_wait();  // everything above (barriers, TMEM, folded constants) overlaps the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -151,16 +151,18 @@ def test_fgmsa_bf16(sj):
     assert max_abs(pos, rpos) < 0.25 and max_abs(y, ry) < 0.1
 
 
-def test_decoder_bf16(sj):
+@pytest.mark.parametrize("B", [1, 3])
+def test_decoder_bf16(sj, B):
+    """B = 3 gives the skip-add GEMMs several tiles per CTA (the residual prefetch crosses tile boundaries)."""
     w = oracle_model()
     dec = sj.Pyramid3DDecoder(None, (256, 256), use_pyramid=True, timestep_split=True, shallow_decode=1,
                               flow_sep_decode=True, conv_cnn=False, dtype="bfloat16")
     dec.set_weights(sub(w, "decoder."))
-    x = _bf(randn((1, 8, 16, 16, 384), 18))
-    res = [_bf(randn((1, 4096, 96), 19)), _bf(randn((1, 4096, 96), 20)), _bf(randn((1, 1024, 192), 21)),
-           _bf(randn((1, 16, 16, 384), 22))]
+    x = _bf(randn((B, 8, 16, 16, 384), 18))
+    res = [_bf(randn((B, 4096, 96), 19)), _bf(randn((B, 4096, 96), 20)), _bf(randn((B, 1024, 192), 21)),
+           _bf(randn((B, 16, 16, 384), 22))]
     out = dec(x, training=False, res_list=res)
     ref = O.decoder_forward(x, res, w)
     err = max_abs(out, ref)
-    print(f"decoder bf16: max abs err {err:.3e}, max |ref| {ref.abs().max().item():.2f}")
+    print(f"decoder bf16 B={B}: max abs err {err:.3e}, max |ref| {ref.abs().max().item():.2f}")
     assert err < 0.05 * ref.abs().max().item()
