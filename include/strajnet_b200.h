@@ -277,6 +277,31 @@ int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, c
                     float* out, const SjModelW* w, int B, int S, int dtype, void* workspace, size_t workspace_bytes,
                     sj_stream_t stream);
 
+/* ---- validation-side ops, forward values only ------------------------------------------
+ * One pass over the grids computes both OGMFlow_loss.__call__ (loss.py:50-170; helpers :172-292) and
+ * compute_occupancy_flow_metrics (occu_metric.py:26-140; helpers :152-343, the zero-border `sample` :345-409), as
+ * val_step uses them (train.py:252-283).
+ *   pred    fp32 [B,H,W,32]   channel 4k+0 / 4k+1 observed / occluded occupancy, 4k+2, 4k+3 flow (train.py:103-121);
+ *                             logits, or probabilities when SJ_EVAL_PRED_IS_PROB (metrics only: the output of
+ *                             _apply_sigmoid_to_occupancy_logits, train.py:142-154)
+ *   gt_obs, gt_occ, origin   fp32 [B,8,H,W]; gt_flow fp32 [B,8,H,W,2]   (train.py:126-140)
+ *   out     fp32 [SJ_EVAL_OUT_FLOATS] (device): [0..3] observed_xe, occluded_xe, flow, flow_warp_xe;
+ *           [4..10] vehicles_observed_auc, vehicles_occluded_auc, vehicles_observed_iou, vehicles_occluded_iou,
+ *           vehicles_flow_epe, vehicles_flow_warped_occupancy_auc, vehicles_flow_warped_occupancy_iou;
+ *           [11..18] the per-waypoint gate `res` of the use_gt branch (loss.py:125-137).
+ * flags: the OGMFlow_loss constructor switches (loss.py:24-25), which of the two results to compute, and
+ * compute_occupancy_flow_metrics' no_warp. */
+enum {
+  SJ_EVAL_USE_FOCAL = 1, SJ_EVAL_NO_USE_WARP = 2, SJ_EVAL_USE_PRED = 4, SJ_EVAL_USE_GT = 8,
+  SJ_EVAL_PRED_IS_PROB = 16, SJ_EVAL_LOSS = 32, SJ_EVAL_METRICS = 64, SJ_EVAL_METRICS_NO_WARP = 128
+};
+#define SJ_EVAL_OUT_FLOATS 19
+typedef struct { int flags; float ogm_weight; float occ_weight; float flow_origin_weight; float replica; } SjEvalParams;
+size_t sj_ogm_flow_eval_workspace_bytes(void);
+int sj_ogm_flow_eval_fwd(const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,
+                         const float* origin, int B, int H, int W, const SjEvalParams* params, float* out,
+                         void* workspace, size_t workspace_bytes, sj_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

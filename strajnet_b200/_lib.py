@@ -76,6 +76,11 @@ class SjIoSpec(C.Structure):
     _fields_ = [("ogm_type", C.c_int), ("map_type", C.c_int), ("out_mode", C.c_int)]
 
 
+class SjEvalParams(C.Structure):
+    _fields_ = [("flags", C.c_int), ("ogm_weight", C.c_float), ("occ_weight", C.c_float),
+                ("flow_origin_weight", C.c_float), ("replica", C.c_float)]
+
+
 class SjModelW(C.Structure):
     _fields_ = [("encoder", SjEncoderW), ("fgmsa", SjFgmsaW), ("traj", SjTrajW), ("decoder", SjDecoderW),
                 ("fg_msa", C.c_int), ("fg", C.c_int), ("large_ogm", C.c_int)]
@@ -123,6 +128,8 @@ SIGNATURES = {
     "sj_strajnet_workspace_bytes": (_sz, [_i, _i, _i]),
     "sj_strajnet_fwd_io": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), C.POINTER(SjIoSpec), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_fwd": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), _i, _i, _i, _p, _sz, _p]),
+    "sj_ogm_flow_eval_workspace_bytes": (_sz, []),
+    "sj_ogm_flow_eval_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, C.POINTER(SjEvalParams), _p, _p, _sz, _p]),
 }
 
 _lib = None

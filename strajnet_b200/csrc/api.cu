@@ -968,4 +968,20 @@ int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, c
   return sj_strajnet_fwd_io(ogm, map_img, flow, obs, occ, out, w, &io, B, S, dtype, workspace, workspace_bytes, stream);
 }
 
+// ---- OGMFlow_loss.__call__ + compute_occupancy_flow_metrics (loss.py:50-170, occu_metric.py:26-140) ----
+size_t sj_ogm_flow_eval_workspace_bytes(void) { return eval_workspace_bytes(); }
+int sj_ogm_flow_eval_fwd(const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,
+                         const float* origin, int B, int H, int W, const SjEvalParams* params, float* out,
+                         void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(pred && gt_obs && gt_occ && gt_flow && origin && params && out && B > 0 && H > 0 && W > 0);
+  SJ_REQUIRE(params->flags & (SJ_EVAL_LOSS | SJ_EVAL_METRICS));
+  // probabilities only make sense for the metrics (the loss is defined on logits)
+  SJ_REQUIRE(!((params->flags & SJ_EVAL_PRED_IS_PROB) && (params->flags & SJ_EVAL_LOSS)));
+  SJ_REQUIRE((long long)B * H * W < (1ll << 24));  // Keras keeps the confusion counts in float32 variables: exact below 2^24
+  return run(workspace, workspace_bytes, SJ_F32, stream, [&](Ctx& c) {
+    eval_forward(c, pred, gt_obs, gt_occ, gt_flow, origin, B, H, W, params->flags, params->ogm_weight, params->occ_weight,
+                 params->flow_origin_weight, params->replica, out);
+  });
+}
+
 }  // extern "C"

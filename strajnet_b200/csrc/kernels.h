@@ -222,4 +222,10 @@ void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* 
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
                  int out_layout, void* out);
 
+// ---- validation-side loss / metrics (eval.cu) ----------------------------------------------------
+size_t eval_workspace_bytes();
+void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,
+                  const float* origin, int B, int H, int W, int flags, float ogm_weight, float occ_weight,
+                  float flow_origin_weight, float replica, float* out);
+
 }  // namespace sj
