@@ -29,12 +29,12 @@ struct EvalP {
 };
 
 __device__ __forceinline__ float sce(float z, float x) {  // tf.nn.sigmoid_cross_entropy_with_logits
-  return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+  return fmaxf(x, 0.f) - x * z + __logf(1.0f + __expf(-fabsf(x)));  // MUFU-grade: the sums are compared at 2e-4
 }
 __device__ __forceinline__ float bce_prob(float z, float p) {  // Keras backend binary_crossentropy, from_logits=False
   const float eps = 1e-7f;
   p = fminf(fmaxf(p, eps), 1.0f - eps);
-  return -(z * logf(p + eps) + (1.0f - z) * logf(1.0f - p + eps));
+  return -(z * __logf(p + eps) + (1.0f - z) * __logf(1.0f - p + eps));
 }
 __device__ __forceinline__ float focal(float z, float prob, float ce) {  // tfa SigmoidFocalCrossEntropy, alpha .25, gamma 2
   const float p_t = z * prob + (1.0f - z) * (1.0f - prob);
@@ -42,7 +42,7 @@ __device__ __forceinline__ float focal(float z, float prob, float ce) {  // tfa 
   const float m = 1.0f - p_t;
   return a_t * (m * m) * ce;
 }
-__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // sample(image, warp, pixel_type=0) with a zero border: pad by 1, warp + 1, floor clamped to [0, size-2], alpha
 // clamped to [0,1] (occu_metric.py:394-409, tfa_image.py:116-171); (wx, wy) = (x, y) source coordinates
@@ -58,17 +58,21 @@ __device__ __forceinline__ float sample_zero(const float* __restrict__ img, int 
 }
 
 // number of AUC thresholds strictly below v (thr[0] = -1e-7, thr[i] = i/99, thr[99] = 1 + 1e-7, all float32)
+// Branch-free: c0 = floor(99 v) is within one of the answer, so three table compares around it settle it exactly
+// (thresholds 0 .. c0-2 are below v for sure, thresholds c0+2 .. are not).  NaN counts no threshold, like `pred > thr`.
 __device__ __forceinline__ int auc_bin(float v, const float* thr) {
-  int c = (int)(v * 99.0f);
-  c = max(0, min(99, c));
-  while (c < 100 && thr[c] < v) ++c;
-  while (c > 0 && !(thr[c - 1] < v)) --c;
-  return c;
+  const int c0 = max(1, min(98, (int)(v * 99.0f)));
+  return (c0 - 1) + (thr[c0 - 1] < v) + (thr[c0] < v) + (thr[c0 + 1] < v);
 }
-// all 32 lanes call; lanes with key < 0 contribute nothing; lanes with equal keys are merged into one atomic
+// all 32 lanes call; lanes with key < 0 contribute nothing.  Occupancy grids are mostly empty, so a warp's 32 cells
+// usually fall into ONE bin: that case costs one vote and one atomic; otherwise every lane adds its own count.
 __device__ __forceinline__ void hist_add(int* h, int key, int lane) {
-  const unsigned m = __match_any_sync(0xffffffffu, key);
-  if (key >= 0 && lane == __ffs(m) - 1) atomicAdd(&h[key], __popc(m));
+  const int first = __shfl_sync(0xffffffffu, key, 0);
+  if (__all_sync(0xffffffffu, key == first)) {
+    if (lane == 0 && key >= 0) atomicAdd(&h[key], 32);
+  } else if (key >= 0) {
+    atomicAdd(&h[key], 1);
+  }
 }
 
 __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
@@ -86,16 +90,18 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
              is_prob = p.flags & SJ_EVAL_PRED_IS_PROB, do_loss = p.flags & SJ_EVAL_LOSS,
              do_metrics = p.flags & SJ_EVAL_METRICS, no_warp_m = p.flags & SJ_EVAL_METRICS_NO_WARP;
   const int HW = p.H * p.W;
-  const long long N = (long long)p.B * HW;
   float acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-  for (long long base = (long long)blockIdx.x * NT; base < N; base += (long long)p.nblk * NT) {
-    const long long idx = base + tid;
-    const bool valid = idx < N;
+  // work item = one image row (b, y) x 256 columns: the index arithmetic is warp-uniform and done once per item
+  const int xchunks = (p.W + NT - 1) / NT, items = p.B * p.H * xchunks;
+  for (int item = blockIdx.x; item < items; item += p.nblk) {
+    const int row = item / xchunks, b = row / p.H, y = row % p.H, x = (item % xchunks) * NT + tid;
+    const bool valid = x < p.W;
     int key[NAUC] = {-1, -1, -1, -1};
     if (valid) {
-      const int b = (int)(idx / HW), pix = (int)(idx % HW), y = pix / p.W, x = pix % p.W;
+      const int pix = y * p.W + x;
+      const long long idx = (long long)b * HW + pix;
       const float4 pr = *reinterpret_cast<const float4*>(p.pred + idx * 32 + 4 * k);
       const long long g = ((long long)b * 8 + k) * HW + pix;
       const float to = p.gt_obs[g], tc = p.gt_occ[g];
@@ -109,11 +115,12 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
       float po = pr.x, pc = pr.y;  // probabilities (metrics); pr.x / pr.y stay the logits for the loss
       if (!is_prob) { po = sigmoidf(pr.x); pc = sigmoidf(pr.y); }
       if (do_loss) {
-        acc[A_OBS_SCE] += sce(to, pr.x);
-        acc[A_OCC_SCE] += sce(tc, pr.y);
+        const float so = sce(to, pr.x), sc = sce(tc, pr.y);
+        acc[A_OBS_SCE] += so;
+        acc[A_OCC_SCE] += sc;
         if (use_focal) {
-          acc[A_OBS_FOCAL] += focal(to, sigmoidf(pr.x), sce(to, pr.x));
-          acc[A_OCC_FOCAL] += focal(tc, sigmoidf(pr.y), sce(tc, pr.y));
+          acc[A_OBS_FOCAL] += focal(to, po, so);  // do_loss implies logits: po / pc are their sigmoids
+          acc[A_OCC_FOCAL] += focal(tc, pc, sc);
         }
         acc[A_FLOW_L1] += fabsf(dx) + fabsf(dy);
         if (use_gt) {
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
           key[3] = (ta != 0.f ? NBIN : 0) + auc_bin(wo * ta, thr_s);
         }
         if (!no_use_warp) {
-          const float a = use_pred ? sigmoidf(pr.x) + sigmoidf(pr.y) : sigmoidf(to) + sigmoidf(tc);
+          const float a = use_pred ? po + pc : sigmoidf(to) + sigmoidf(tc);
           const float joint = fminf(fmaxf(a, 0.f), 1.f) * wp;
           const float bce = bce_prob(ta, joint);
           acc[A_WARP_BCE] += bce;
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(256) eval_finalize_kernel(const FinP p) {
   for (int i = 0; i < 7; ++i) p.out[4 + i] = m[i] / 8.0f;
 }
 
-int eval_blocks() { return 2 * num_sms() / 8 > 0 ? 2 * num_sms() / 8 : 1; }
+int eval_blocks() { return 4 * num_sms() / 8 > 0 ? 4 * num_sms() / 8 : 1; }  // per waypoint: 4 blocks per SM in all
 
 }  // namespace
 

@@ -2,7 +2,9 @@
 //
 //   * persistent: grid = #SMs, each CTA strides over (group, m-tile, n-tile) work items;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer,
-//     warps 2..5 = epilogue (TMEM lane quarter = warp % 4);
+//     warps 2.. = epilogue (TMEM lane quarter = warp % 4; EW = 8 or 16 epilogue warps, i.e. 2 or 4 warps per quarter,
+//     each taking a share of the columns: the epilogue is a chain of TMEM / global-memory round trips and more
+//     resident warps hide it);
 //   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B, 64-element K blocks) through a
 //     4-stage mbarrier ring; accumulators live in TMEM (fp32, 128 lanes x BN columns), double
 //     buffered so the epilogue of tile i overlaps the main loop of tile i+1;
@@ -22,7 +24,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int nthreads(int ew) { return 64 + 32 * ew; }  // TMA warp, MMA warp, EW epilogue warps
 constexpr int A_STAGE_BYTES_MAX = 256 * BK * 2;
 
 struct KParams {
@@ -55,8 +58,8 @@ struct KParams {
 // RPF (residual prefetch): the residual rows of tile i+1 are fetched into registers while tile i is in its epilogue
 // (each 32-column chunk is re-loaded for the next tile right after it has been consumed), so the epilogue never sits
 // on a global-memory round trip.  Needs 32-column chunks only and at most 96 columns per thread.
-template <int ACT, bool LN, bool RPF = false>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int ACT, bool LN, bool RPF = false, int EW = 8>
+__global__ void __launch_bounds__(nthreads(EW), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,8 +73,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float2* stat_s = reinterpret_cast<float2*>(bars + 32);  // [2 accumulator stages][128 rows] partial (sum, sum of squares)
-  float* vec_s = reinterpret_cast<float*>(stat_s + 2 * BM);  // [bias: vec_smem floats][column sums: vec_smem floats]
+  constexpr int NTHREADS = nthreads(EW), NSUB = EW / 4;  // NSUB warps share each TMEM lane quarter
+  float2* stat_s = reinterpret_cast<float2*>(bars + 32);  // [2 accumulator stages][4 column shares][128 rows] partial (sum, sum of squares)
+  float* vec_s = reinterpret_cast<float*>(stat_s + 2 * 4 * BM);  // [bias: vec_smem floats][column sums: vec_smem floats]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -83,7 +87,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], EW);
     }
     fence_barrier_init();
   }
@@ -160,9 +164,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    const int quarter = warp % 4, half = (warp - 2) / 4;  // two warps per TMEM lane quarter, each takes half the columns
-    const int csplit = ((p.BN / 16 + 1) / 2) * 16;
-    const int c_begin = half ? csplit : 0, c_end = half ? p.BN : csplit;
+    // NSUB warps per TMEM lane quarter; the BN/16 column units are dealt out as evenly as possible, low shares first
+    const int quarter = warp % 4, sub = (warp - 2) / 4;
+    const int n16 = p.BN / 16, ubase = n16 / NSUB, urem = n16 % NSUB;
+    const int c_begin = 16 * (sub * ubase + min(sub, urem)), c_end = c_begin + 16 * (ubase + (sub < urem ? 1 : 0));
     if (p.vec_smem) {
       // per-column epilogue vectors: staged once, then read as shared-memory broadcasts (global loads of them miss L1
       // behind the streaming residual / output traffic and show up as long-scoreboard stalls)
@@ -171,7 +176,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         vec_s[i] = p.bias ? p.bias[i] : 0.f;
         if (LN) vec_s[p.vec_smem + i] = p.ln_s[i];
       }
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, %0;" ::"n"(EW * 32) : "memory");
     }
     int as = 0;
     uint32_t aphase = 0;
@@ -304,12 +309,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (c < c_end) chunk(std::integral_constant<int, 16>{}, c, std::integral_constant<int, 0>{});
       }
       if (p.st_mean) {
-        // the two warps of a TMEM lane quarter each hold half of the row: combine through shared memory
+        // the warps of a TMEM lane quarter each hold a share of the row: combine through shared memory (fixed order)
         const int rloc = quarter * 32 + lane;
-        if (half) stat_s[as * BM + rloc] = make_float2(st_s, st_q);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        if (!half && valid) {
-          const float2 o2 = stat_s[as * BM + rloc];
+        if (sub) stat_s[(as * 4 + sub) * BM + rloc] = make_float2(st_s, st_q);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(NSUB * 32) : "memory");
+        if (!sub && valid) {
+          float2 o2 = stat_s[(as * 4 + 1) * BM + rloc];
+#pragma unroll
+          for (int q = 2; q < NSUB; ++q) {
+            const float2 t = stat_s[(as * 4 + q) * BM + rloc];
+            o2.x += t.x;
+            o2.y += t.y;
+          }
           const float mu = (st_s + o2.x) / (float)p.N;
           const float var = fmaxf((st_q + o2.y) / (float)p.N - mu * mu, 0.f);
           p.st_mean[crow] = mu;
@@ -452,7 +463,7 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     c.fail(SJ_ECUDA);
     return;
   }
-  size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * BM * sizeof(float2);
+  size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * 4 * BM * sizeof(float2);
   {
     // stage the per-column vectors when they are dense ([groups][N]) and fit beside the operand ring
     const int vec = p.groups * a.N;
@@ -468,19 +479,29 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
   const size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;
   const bool ln = a.ln_mean != nullptr;
-#define SJ_TCG(ACT_, LN_, RPF_)                                                                                       \
+#define SJ_TCG2(ACT_, LN_, RPF_, EW_)                                                                                 \
   do {                                                                                                                \
-    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_, RPF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_, RPF_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                              227 * 1024) != cudaSuccess) {                                                            \
       c.fail(SJ_ECUDA);                                                                                               \
       return;                                                                                                         \
     }                                                                                                                 \
-    SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_, RPF_>), grid, NTHREADS, smem_launch, mapA, mapB, p);           \
+    SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_, RPF_, EW_>), grid, nthreads(EW_), smem_launch, mapA, mapB, p); \
+  } while (0)
+  // Two experiment knobs, both measured neutral on B200 at batch 16 and therefore off by default:
+  // SJ_TCG_EW=16: 16 epilogue warps (4 per TMEM lane quarter; needs >= 16 columns per warp);
+  // SJ_TCG_RPF=1: the residual-prefetch epilogue (145+ registers: 8 warps only).
+  static const bool ew16_on = getenv("SJ_TCG_EW") != nullptr && atoi(getenv("SJ_TCG_EW")) == 16;
+  static const bool rpf_on = getenv("SJ_TCG_RPF") != nullptr;
+  const bool ew16 = ew16_on && p.BN >= 64;
+#define SJ_TCG(ACT_, LN_, RPF_)                    \
+  do {                                             \
+    if (ew16 && !(RPF_)) SJ_TCG2(ACT_, LN_, false, 16); \
+    else SJ_TCG2(ACT_, LN_, RPF_, 8);              \
   } while (0)
   // residual prefetch: both column halves of a tile must be whole 32-column chunks, at most three per thread
   const int csplit = ((p.BN / 16 + 1) / 2) * 16, w0 = csplit, w1 = p.BN - csplit;
-  static const bool rpf_off = getenv("SJ_NO_RPF") != nullptr;
-  const bool rpf = a.R && !ln && !rpf_off && w0 % 32 == 0 && w1 % 32 == 0 && w0 <= 96 && w1 <= 96 && w1 > 0;
+  const bool rpf = rpf_on && a.R && !ln && w0 % 32 == 0 && w1 % 32 == 0 && w0 <= 96 && w1 <= 96 && w1 > 0;
   if (a.act == ACT_GELU) { if (ln) SJ_TCG(ACT_GELU, true, false); else SJ_TCG(ACT_GELU, false, false); }
   else if (a.act == ACT_ELU) {
     if (ln) SJ_TCG(ACT_ELU, true, false);
@@ -491,6 +512,7 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     else if (rpf) SJ_TCG(ACT_NONE, false, true);
     else SJ_TCG(ACT_NONE, false, false);
   }
+#undef SJ_TCG2
 #undef SJ_TCG
 }
 

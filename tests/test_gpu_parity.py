@@ -454,3 +454,16 @@ def test_programmatic_dependent_launch_is_invisible(sj, dtype):
         s.synchronize()
     finally:
         lib.sj_set_pdl(prev)
+
+
+def test_headline_batch16_bf16_batch_invariance(sj):
+    """BASELINE config 3 at full size (batch 16, bf16) through a size-independent property: every sample of the batch
+    equals the same sample run alone, bit for bit (no cross-sample op anywhere in the path), for the logits
+    and for the fused submission quantisation."""
+    m = _model(sj, dtype="bfloat16")
+    inp = O.make_inputs(16, 256, seed=71)
+    y = _fwd(m, inp)
+    assert tuple(y.shape) == (16, 256, 256, 32) and torch.isfinite(y).all()
+    for i in (0, 7, 15):
+        one = {k: v[i:i + 1] for k, v in inp.items()}
+        assert torch.equal(_fwd(m, one)[0], y[i]), f"sample {i} differs between batch 16 and batch 1"

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch16" 2>&1 | tail -5
+timeout 300 python tools/eval_bench.py 2>&1 | tail -3 | tee gpurun_out/t5_eval_bench.json
