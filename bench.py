@@ -32,8 +32,8 @@ UNIT = "frames/s"
 PROBE_ROLE = "dec.upconv3"
 PROBE_GFLOP_PER_FRAME_NOMINAL = 2 * 8 * 65536 * 9 * 96 * 48 / 1e9
 PROBE_GFLOP_PER_FRAME = 2 * 8 * 65536 * 4 * 96 * 48 / 1e9
-# DRAM bytes of that launch at batch 16 from `ncu --set full` (profiles/r01e_ncu_full_tc_kernels.md): read + write
-PROBE_DRAM_BYTES_B16 = 403.2e6 + 751.5e6
+# DRAM bytes of that launch at batch 16 from `ncu --set full` (profiles/r01f_ncu_full_tc_kernels.md, launch 11): read + write
+PROBE_DRAM_BYTES_B16 = 407.8e6 + 752.9e6
 
 
 def synth_inputs(B, S=256, seed=0):
