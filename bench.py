@@ -192,15 +192,16 @@ def main():
     devin = {k: v.to(dev) for k, v in host.items()}
     out = torch.empty(B, 256, 256, 32, dtype=torch.float32, device=dev)
 
-    from strajnet_b200.parallel import gather_outputs
+    from strajnet_b200.parallel import gather_outputs, make_gatherer
     from strajnet_b200.pipeline import InferencePipeline
 
     # N > 1: the single collective of the path (config 4) runs on a side stream over double-buffered output
-    # grids, so the all-gather of step i overlaps the forward of step i+1
-    outs = [out, torch.empty_like(out)] if world > 1 else [out]
-    comm = torch.cuda.Stream(dev) if world > 1 else None
+    # grids, so the all-gather of step i overlaps the forward of step i+1.  The gatherer moves the shards with the copy
+    # engines over NVLink peer memory when every rank can (strajnet_b200/parallel.py), else with NCCL.
+    gatherer = make_gatherer(tuple(out.shape), out.dtype, dev, slots=2) if world > 1 else None
+    outs = [gatherer.shard(0), gatherer.shard(1)] if world > 1 else [out]
     ev_done = [torch.cuda.Event() for _ in outs]
-    ev_gathered = [torch.cuda.Event() for _ in outs]
+    ev_gathered = [None for _ in outs]
     state = {"k": 0}
 
     def step_resident(graph=True):
@@ -209,19 +210,16 @@ def main():
         s = state["k"] % len(outs)
         state["k"] += 1
         cur = torch.cuda.current_stream()
-        if world > 1:
-            cur.wait_event(ev_gathered[s])
+        if world > 1 and ev_gathered[s] is not None:
+            cur.wait_event(ev_gathered[s])  # the previous gather of this slot has read the shard everywhere
         model.forward_into(outs[s], devin["ogm"], devin["map_img"], devin["obs"], devin["occ"], devin["flow"], graph=graph)
         if world > 1:
             ev_done[s].record(cur)
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev_done[s])
-                gather_outputs(outs[s])
-                ev_gathered[s].record(comm)
+            ev_gathered[s] = gatherer.gather(s, ev_done[s])
 
     def drain():
         if world > 1:
-            torch.cuda.current_stream().wait_stream(comm)
+            torch.cuda.current_stream().wait_stream(gatherer.stream)
 
     # end to end through the public serving API: every step copies its inputs from pinned host memory to the
     # device and its logits back to pinned host memory; copies of neighbouring steps overlap the forward
@@ -356,7 +354,8 @@ def main():
                        "weights": "random init (Keras default initialisers)",
                        "launch": "one CUDA graph replay per step (captured from the library's stream launches)",
                        "l2": "per-step inputs (113 MB) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush",
-                       "collective": "one NCCL all-gather of the fp32 output grids per step, on a side stream overlapping the next forward" if world > 1 else "none"},
+                       "collective": (f"one all-gather of the fp32 output grids per step ({gatherer.kind}), on a side stream "
+                                      "overlapping the next forward") if world > 1 else "none"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,

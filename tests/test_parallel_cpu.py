@@ -52,6 +52,14 @@ def _worker(rank, world, port, q):
         ok = tuple(y.shape) == (B, 4, 4, 32) and torch.equal(y, ref)
         sh = P.shard_inputs(inp, rank, world)
         ok = ok and sh["ogm"].shape[0] == B // world
+        # the slot-based gatherer bench.py / serving use: on CPU (gloo) make_gatherer must give the plain all-gather path
+        ag = P.make_gatherer((3, 4, 4, 32), torch.float32, "cpu", slots=2)
+        ok = ok and isinstance(ag, P.NcclAllGather)
+        for s in range(2):
+            ag.shard(s).fill_(float(10 * s + rank + 1))
+            ag.gather(s)
+            want = torch.cat([torch.full((3, 4, 4, 32), float(10 * s + r + 1)) for r in range(world)])
+            ok = ok and torch.equal(ag.full[s], want)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
