@@ -93,3 +93,48 @@ def test_layer_argument_validation():
         sj.SwinTransformerBlock(32, (64, 64), 2, window_size=8, shift_size=8, device="cpu")
     blk = sj.SwinTransformerBlock(32, (4, 4), 2, window_size=8, shift_size=4, device="cpu")
     assert blk.window_size == 4 and blk.shift_size == 0  # modules.py:173-175
+
+
+def test_evaluation_host_logic():
+    """Row f4 host side (no GPU): the WaypointGrids container packs to the kernel's layouts exactly as train.py:103-140
+    slices them, the constructor switches map to the C-ABI flag bits, and CPU tensors are refused (no CPU fallback)."""
+    import pytest
+    import torch
+    from strajnet_b200 import _lib as L
+    from strajnet_b200 import evaluation as V
+    from strajnet_b200.loss import OGMFlow_loss
+    from strajnet_b200.occu_metric import WaypointGrids, compute_occupancy_flow_metrics  # noqa: F401
+
+    g = torch.Generator().manual_seed(0)
+    out = torch.randn(2, 8, 8, 32, generator=g)
+    gt = dict(obs=torch.rand(2, 8, 8, 8, 1, generator=g), occ=torch.rand(2, 8, 8, 8, 1, generator=g),
+              flow=torch.randn(2, 8, 8, 8, 2, generator=g), org=torch.rand(2, 8, 8, 8, 1, generator=g))
+    pred, true = WaypointGrids(), WaypointGrids()
+    for k in range(8):  # train.py:103-121 and :126-140
+        c = out[:, :, :, 4 * k: 4 * k + 4]
+        pred.vehicles.observed_occupancy.append(c[:, :, :, :1])
+        pred.vehicles.occluded_occupancy.append(c[:, :, :, 1:2])
+        pred.vehicles.flow.append(c[:, :, :, 2:])
+        true.vehicles.observed_occupancy.append(gt["obs"][:, k])
+        true.vehicles.occluded_occupancy.append(gt["occ"][:, k])
+        true.vehicles.flow.append(gt["flow"][:, k])
+        true.vehicles.flow_origin_occupancy.append(gt["org"][:, k])
+    assert torch.equal(V.pack_predictions(pred, device="cpu"), out)
+    o, c, f, r = V.pack_truth(true, device="cpu")
+    assert torch.equal(o, gt["obs"][..., 0]) and torch.equal(c, gt["occ"][..., 0])
+    assert torch.equal(f, gt["flow"]) and torch.equal(r, gt["org"][..., 0])
+    pred.vehicles.flow.pop()
+    with pytest.raises(ValueError):
+        V.pack_predictions(pred, device="cpu")
+    # flag bits = the enum of include/strajnet_b200.h
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "strajnet_b200.h")).read()
+    for name, bit in (("USE_FOCAL", "use_focal"), ("NO_USE_WARP", "no_use_warp"), ("USE_PRED", "use_pred"), ("USE_GT", "use_gt"),
+                      ("PRED_IS_PROB", "pred_is_prob"), ("LOSS", "loss"), ("METRICS", "metrics"),
+                      ("METRICS_NO_WARP", "metrics_no_warp")):
+        assert f"SJ_EVAL_{name} = {V.FLAG[bit]}" in hdr
+    assert f"#define SJ_EVAL_OUT_FLOATS {V.OUT_FLOATS}" in hdr
+    assert OGMFlow_loss(None).flags() == V.FLAG["use_focal"]  # reference defaults (loss.py:24-25)
+    assert OGMFlow_loss(None, use_gt=True, use_focal_loss=False, no_use_warp=True).flags() == V.FLAG["use_gt"] | V.FLAG["no_use_warp"]
+    assert C.sizeof(L.SjEvalParams) == 20
+    with pytest.raises(RuntimeError):
+        OGMFlow_loss(None).packed(out, o, c, f, r)  # CPU tensors: the op runs on the GPU or raises
