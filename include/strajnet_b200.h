@@ -16,7 +16,8 @@
  *   - `dtype` selects the activation type of `x`/`y`/intermediates (SJ_F32 or SJ_BF16);
  *     model inputs (rasters, actors) are always fp32; weights are fp32 ([in,out] Keras layout)
  *     with an optional bf16 tensor-core copy (`w_tc`, [out,in] K-major) used when dtype==SJ_BF16;
- *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state;
+ *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state that results depend on
+ *     (the launch-mode mask of sj_set_pdl and the per-thread timing probe are the only knobs, both opt-in);
  *     the caller owns all buffers including `workspace`; safe to capture in a CUDA graph;
  *   - return 0 (SJ_OK) or a negative SjStatus; never throws.
  */
