@@ -1,6 +1,6 @@
 """Generate the golden fixtures under tests/golden/ (run in the build container only).
 
-Two kinds of pins:
+Three kinds of pins:
  1. ``ref_index_maps.npz`` -- integer maps produced by executing the reference's OWN pure-NumPy
     lines verbatim (text read from /root/reference/modules.py at generation time, never copied
     into this repo): ``relative_position_index`` (modules.py:88-98) and the shifted-window region
@@ -9,6 +9,8 @@ Two kinds of pins:
  2. ``oracle_outputs.npz`` -- subsampled outputs of oracle/strajnet_oracle.py on seeded inputs, so a
     later edit of the oracle that changes its numbers is caught.  (The reference itself cannot
     run here: no TensorFlow.  See the oracle header, "parity unpinned".)
+ 3. ``eval_outputs.npz`` -- the same drift guard for oracle/eval_oracle.py (validation-side loss / metrics);
+    ``--eval-only`` regenerates just this file.
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -84,5 +86,28 @@ def main():
     print({k: v.shape for k, v in gold.items()})
 
 
+EVAL_FLAGS = {"default": dict(), "train_py": dict(use_gt=True, use_focal_loss=False), "use_pred": dict(use_pred=True)}
+
+
+def eval_golden():
+    """``eval_outputs.npz`` -- drift guard for oracle/eval_oracle.py (row f4): the four losses for three constructor
+    configurations and the seven metrics on the seeded synthetic batch (B = 2, 64 x 64)."""
+    from oracle import eval_oracle as E
+    d = E.make_eval_inputs(2, 64, seed=0)
+    gold = {}
+    for name, flags in EVAL_FLAGS.items():
+        r = E.ogm_flow_loss(**d, **flags)
+        gold[f"loss_{name}"] = np.array([r[k].item() for k in ("observed_xe", "occluded_xe", "flow", "flow_warp_xe")], np.float64)
+    m = E.occupancy_flow_metrics(**d)
+    gold["metrics"] = np.array([v.item() for v in m.values()], np.float64)
+    np.savez_compressed(os.path.join(HERE, "eval_outputs.npz"), **gold)
+    print({k: v.tolist() for k, v in gold.items()})
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--eval-only" in sys.argv:
+        eval_golden()
+    else:
+        main()
+        eval_golden()

@@ -100,3 +100,16 @@ def test_loss_and_metrics_structure():
     assert all(torch.isfinite(v) for v in E.occupancy_flow_metrics(**empty).values())
     # use_gt with every waypoint gated off: 0 / 0, as tf.math.add_n(...) / add_n(f_c) gives
     assert torch.isnan(E.ogm_flow_loss(**empty, use_gt=True)["flow"])
+
+
+def test_eval_oracle_matches_golden(golden_dir):
+    """Drift guard: tests/golden/eval_outputs.npz (tests/golden/make_golden.py --eval-only)."""
+    g = np.load(f"{golden_dir}/eval_outputs.npz")
+    d = E.make_eval_inputs(2, 64, seed=0)
+    flags = {"default": dict(), "train_py": dict(use_gt=True, use_focal_loss=False), "use_pred": dict(use_pred=True)}
+    for name, f in flags.items():
+        r = E.ogm_flow_loss(**d, **f)
+        got = np.array([r[k].item() for k in ("observed_xe", "occluded_xe", "flow", "flow_warp_xe")])
+        np.testing.assert_allclose(got, g[f"loss_{name}"], rtol=2e-5)
+    m = E.occupancy_flow_metrics(**d)
+    np.testing.assert_allclose(np.array([v.item() for v in m.values()]), g["metrics"], rtol=2e-5)
