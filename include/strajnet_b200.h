@@ -261,6 +261,22 @@ int sj_decoder_fwd(const void* x, const void* flow_res, const void* res0, const 
                    const SjDecoderW* w, int B, int out_layout, int dtype, void* workspace, size_t workspace_bytes,
                    sj_stream_t stream);
 
+/* Single decoder stages, exported so that each tensor-core kernel has its own parity test.
+ * One up-sampling stage, modules.py:746-749 (`UpSampling3D((1,2,2))` then `upconv_0s[i]` = Conv2D 3x3 SAME + ELU, shared
+ * over the leading dims): x [NB,H,H,Cin] -> y [NB,2H,2H,Cout]. */
+int sj_upconv_fwd(const void* x, void* y, const SjLinear* w, int NB, int H, int Cin, int Cout, int dtype,
+                  sj_stream_t stream);
+/* One skip connection, modules.py:750-757 (`res_layer[i]` = Conv3D (8,1,1) + ELU over the 8x-repeated skip tensor, then
+ * add), with the collapsed per-waypoint kernels of SjDecoderW.res: dst[b,t] = src[b,t] + ELU(skip[b] . W_eff[t] + bias);
+ * skip [B,HW,Cin], src/dst [B,8,HW,Cout] (dst may alias src). */
+int sj_res_add_fwd(const void* skip, const void* src, void* dst, const SjLinear* w, int B, int HW, int Cin, int Cout,
+                   int dtype, sj_stream_t stream);
+/* The two heads, modules.py:767-770 (`output_layer` on x, `output_layer_f` on the flow branch, Conv2D 3x3 SAME 48->2,
+ * concatenated) + the transpose of :838: x_occ, x_flow [B*8,256,256,48] -> out; out_layout 0/1 as sj_decoder_fwd,
+ * 2 = quantised submission bytes uint8 [B,256,256,32] (inference.py:124-136,160-182). */
+int sj_out_head_fwd(const void* x_occ, const void* x_flow, void* out, const SjDecoderW* w, int B, int out_layout,
+                    int dtype, sj_stream_t stream);
+
 /* Raw I/O of the serving loop.  Inputs as the reference's record decode holds them before the
  * float casts (inference.py:91-93): ogm bool bytes [B,S,S,11,2] (SJ_IN_U8: nonzero -> 1.0), map int8 [B,256,256,3]
  * (SJ_IN_I8_DIV256: value/256).  out_mode 1 fuses the submission quantisation (inference.py:124-136,160-182) into the

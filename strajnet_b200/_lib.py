@@ -125,6 +125,9 @@ SIGNATURES = {
     "sj_traj_cross_attention_fwd": (_i, [_p, _p, _p, _p, C.POINTER(SjTrajW), _i, _i, _p, _sz, _p]),
     "sj_decoder_workspace_bytes": (_sz, [_i, _i]),
     "sj_decoder_fwd": (_i, [_p, _p, _p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p, _sz, _p]),
+    "sj_upconv_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
+    "sj_res_add_fwd": (_i, [_p, _p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
+    "sj_out_head_fwd": (_i, [_p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p]),
     "sj_strajnet_workspace_bytes": (_sz, [_i, _i, _i]),
     "sj_strajnet_fwd_io": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), C.POINTER(SjIoSpec), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_fwd": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), _i, _i, _i, _p, _sz, _p]),

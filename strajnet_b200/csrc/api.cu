@@ -941,6 +941,26 @@ int sj_decoder_fwd(const void* x, const void* flow_res, const void* res0, const 
              [&](Ctx& c) { decoder_impl(c, x, flow_res, res0, res1, out, *w, B, out_layout); });
 }
 
+// ---- single decoder stages (the units the per-kernel parity tests exercise) ----
+int sj_upconv_fwd(const void* x, void* y, const SjLinear* w, int NB, int H, int Cin, int Cout, int dtype,
+                  sj_stream_t stream) {
+  SJ_REQUIRE(x && y && w && w->w && w->b && NB > 0 && H > 0 && Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) { upconv(c, x, y, *w, NB, H, Cin, Cout); });
+}
+int sj_res_add_fwd(const void* skip, const void* src, void* dst, const SjLinear* w, int B, int HW, int Cin, int Cout,
+                   int dtype, sj_stream_t stream) {
+  SJ_REQUIRE(skip && src && dst && w && w->w && w->b && B > 0 && HW > 0 && Cin % 8 == 0 && Cout % 8 == 0);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) { res_add(c, skip, *w, src, dst, B, HW, Cin, Cout); });
+}
+int sj_out_head_fwd(const void* x_occ, const void* x_flow, void* out, const SjDecoderW* w, int B, int out_layout,
+                    int dtype, sj_stream_t stream) {
+  SJ_REQUIRE(x_occ && x_flow && out && w && w->out_w && w->out_b && B > 0 && out_layout >= 0 && out_layout <= 2);
+  return run(nullptr, 0, dtype, stream, [&](Ctx& c) {
+    if (c.dtype == SJ_BF16 && w->out_w_tc) tc_out_conv(c, x_occ, x_flow, w->out_w_tc, w->out_b, B, out_layout, out);
+    else out_conv(c, x_occ, x_flow, w->out_w, w->out_b, B, out_layout, out);
+  });
+}
+
 // ---- STrajNet ----
 size_t sj_strajnet_workspace_bytes(int B, int S, int dtype) {
   SjSwinBlockW zb[2] = {};

@@ -1,0 +1,181 @@
+"""Tight per-kernel parity tests of the tcgen05 (bf16) decoder kernels.
+
+Each kernel is called on its own through the C ABI and compared with a plain fp32 torch computation on the SAME
+bf16-rounded operands (inputs, and the tensor-core copy of the weights exactly as the packer builds it), so the only
+differences left are fp32 accumulation order and ONE rounding of the output:
+
+    |y - ref| <= 2^-8 * |ref| + 1e-3        (bf16 outputs; fp32 outputs: 1e-3 abs)
+
+asserted separately on the interior, the four image borders and the four corners (a wrong border tap of one sub-pixel
+phase changes edge pixels by ~1/9 of their value: far outside this gate, invisible to a 5 %-of-range gate), at the real
+decoder resolutions with >= 2 tiles per CTA.  Reference ops: modules.py:746-749 (up-sampling stage), :750-757 (skip
+add), :767-770 (heads)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import strajnet_oracle as O
+from tests.util import oracle_model, randn, sub
+
+pytestmark = pytest.mark.gpu
+
+REL, ABS = 2.0 ** -8, 1e-3
+
+
+@pytest.fixture(scope="module")
+def env():
+    import strajnet_b200  # noqa: F401
+    from strajnet_b200 import _lib, weights
+    return _lib, weights, torch.device("cuda")
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _regions(H, W):
+    """name -> boolean [H,W] mask: interior, 4 borders (without corners), 4 corners."""
+    m = {}
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    top, bot, lef, rig = yy == 0, yy == H - 1, xx == 0, xx == W - 1
+    m["interior"] = ~(top | bot | lef | rig)
+    m["top"], m["bottom"], m["left"], m["right"] = top & ~lef & ~rig, bot & ~lef & ~rig, lef & ~top & ~bot, rig & ~top & ~bot
+    m["corner_tl"], m["corner_tr"], m["corner_bl"], m["corner_br"] = top & lef, top & rig, bot & lef, bot & rig
+    return m
+
+
+def _assert_tight(y, ref, what, rel=REL, abs_=ABS):
+    """y, ref: [N,H,W,C] (cpu fp32).  Per-region check of |y-ref| <= rel*|ref| + abs_."""
+    assert torch.isfinite(y).all(), f"{what}: non-finite output"
+    excess = (y - ref).abs() - (rel * ref.abs() + abs_)
+    N, H, W, _ = ref.shape
+    for name, mask in _regions(H, W).items():
+        e = excess[:, mask]
+        worst = e.max().item()
+        assert worst <= 0, (f"{what}: region '{name}' exceeds one output rounding by {worst:.3e} "
+                            f"(max |err| there {(y - ref).abs()[:, mask].max().item():.3e})")
+
+
+def subpixel_upconv_ref(x, w_tc, bias):
+    """fp32 reference of nearest-x2 + 3x3 SAME conv + bias + ELU in the folded formulation the kernels execute, using the
+    tensor-core weight copy itself: x [N,H,W,Ci] fp32 (bf16-valued), w_tc [4 phases][Co][4 taps * Ci] fp32 (bf16-valued).
+    out[2y+py, 2x+px] = sum_ab Wf[py,px,a,b] . L[y-1+py+a, x-1+px+b]  (weights.fold_upconv_subpixel)."""
+    N, H, W_, Ci = x.shape
+    Co = w_tc.shape[1]
+    xp = F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1))                       # [N,Ci,H+2,W+2]
+    out = torch.empty(N, Co, 2 * H, 2 * W_)
+    for py in range(2):
+        for px in range(2):
+            k = w_tc[py * 2 + px].reshape(Co, 2, 2, Ci).permute(0, 3, 1, 2)  # [Co,Ci,a,b]
+            c = F.conv2d(xp, k)                                           # [N,Co,H+1,W+1]
+            out[:, :, py::2, px::2] = c[:, :, py:py + H, px:px + W_]
+    return O.elu(out.permute(0, 2, 3, 1) + bias)
+
+
+# (Cin, Cout, H, NB, kernel that must run): NB gives every persistent CTA >= 2 tiles
+UPCONV_CASES = [
+    (96, 48, 128, 3, "tc_upconv4"),     # dec.upconv3 / upconvf1: 384 tiles of 16x8 over 148 CTAs
+    (128, 96, 64, 5, "tc_upconv1p"),    # dec.upconv2 / upconvf0
+    (192, 128, 32, 8, "tc_upconv"),     # dec.upconv1
+    (384, 192, 16, 16, "tc_upconv"),    # dec.upconv0
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,H,NB,kernel", UPCONV_CASES)
+def test_upconv_stage_tight(env, Cin, Cout, H, NB, kernel):
+    _lib, weights, dev = env
+    lib = _lib.lib()
+    torch.backends.cudnn.allow_tf32 = False
+    k = randn((3, 3, Cin, Cout), 31, (6.0 / (9 * Cin + 9 * Cout)) ** 0.5)
+    b = randn((Cout,), 32, 0.1)
+    x = _bf(randn((NB, H, H, Cin), 33))
+    p = weights.Packer({"kernel": k, "bias": b}, dev, tc=True)
+    lin = p._upconv("")
+    w_tc = _bf(weights.fold_upconv_subpixel(k).reshape(4, 4 * Cin, Cout).transpose(1, 2).contiguous())
+    xd = x.to(dev, torch.bfloat16)
+    y = torch.empty(NB, 2 * H, 2 * H, Cout, dtype=torch.bfloat16, device=dev)
+    lib.sj_tc_launch_count(1)
+    _lib.check(lib.sj_upconv_fwd(xd.data_ptr(), y.data_ptr(), C.byref(lin), NB, H, Cin, Cout, _lib.SJ_BF16, _stream()),
+               kernel)
+    torch.cuda.synchronize()
+    assert lib.sj_tc_launch_count(1) == 1, "the tcgen05 up-convolution did not run (silent fallback)"
+    ref = subpixel_upconv_ref(x, w_tc, b)
+    _assert_tight(y.float().cpu(), ref, f"{kernel} {Cin}->{Cout} @{H}")
+    # and against the literal op with fp32 weights (reference formulation): only the bf16 rounding of the folded
+    # weights is added (sqrt(4*Cin) terms of relative 2^-9)
+    lit = O.elu(O.conv2d_nhwc(O._up2(x), k, b, padding="same"))
+    assert (y.float().cpu() - lit).abs().max().item() < 2.5e-2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "quantised"])
+def test_out_heads_tight(env, mode):
+    """tc_outconv: both 3x3 48->2 heads + transpose (+ fused submission quantisation), B = 2 (512 tiles)."""
+    _lib, weights, dev = env
+    lib = _lib.lib()
+    w = oracle_model()
+    B = 2
+    dw = sub(w, "decoder.")
+    p = weights.Packer(dw, dev, tc=True)
+    dec = p.decoder("")
+    xo = _bf(randn((B * 8, 256, 256, 48), 41))
+    xf = _bf(randn((B * 8, 256, 256, 48), 42))
+    xod, xfd = xo.to(dev, torch.bfloat16), xf.to(dev, torch.bfloat16)
+    layout = 2 if mode == "quantised" else 1
+    out = torch.empty(B, 256, 256, 32, dtype=torch.uint8 if layout == 2 else torch.float32, device=dev)
+    lib.sj_tc_launch_count(1)
+    _lib.check(lib.sj_out_head_fwd(xod.data_ptr(), xfd.data_ptr(), out.data_ptr(), C.byref(dec), B, layout, _lib.SJ_BF16,
+                                   _stream()), "tc_out_conv")
+    torch.cuda.synchronize()
+    assert lib.sj_tc_launch_count(1) >= 1
+    # same operands: bf16-rounded head kernels (the tensor-core copy), fp32 biases
+    ko, kf = _bf(dw["output_layer.kernel"]), _bf(dw["output_layer_f.kernel"])
+    occ = O.conv2d_nhwc(xo, ko, dw["output_layer.bias"], padding="same")
+    fl = O.conv2d_nhwc(xf, kf, dw["output_layer_f.bias"], padding="same")
+    ref = torch.cat([occ, fl], -1).reshape(B, 8, 256, 256, 4).permute(0, 2, 3, 1, 4).reshape(B, 256, 256, 32)
+    if layout == 1:
+        _assert_tight(out.cpu(), ref, "tc_outconv fp32", rel=0.0, abs_=1e-3)
+    else:
+        # bytes may differ by one step only where the fp32 logit sits within 1e-3 of a rounding boundary
+        q = out.cpu().to(torch.int16)
+        qr = O.quantize_outputs(ref).to(torch.int16)
+        lo = O.quantize_outputs(ref - 1e-3).to(torch.int16)
+        hi = O.quantize_outputs(ref + 1e-3).to(torch.int16)
+        ok = (q == qr) | (q == lo) | (q == hi)
+        assert ok.all(), f"{(~ok).sum().item()} quantised bytes differ beyond a 1e-3 logit perturbation"
+        assert (q != qr).float().mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,HW,B", [(192, 192, 1024, 3), (96, 128, 4096, 3)])
+def test_res_add_tight(env, Cin, Cout, HW, B):
+    """Grouped skip-add tc_gemm (collapsed (8,1,1) Conv3D + ELU + residual), several tiles per CTA."""
+    _lib, weights, dev = env
+    lib = _lib.lib()
+    k = randn((8, 1, 1, Cin, Cout), 51, (6.0 / (8 * Cin + 8 * Cout)) ** 0.5)
+    b = randn((Cout,), 52, 0.1)
+    p = weights.Packer({"kernel": k, "bias": b}, dev, tc=True)
+    lin = p._res("")
+    skip = _bf(randn((B, HW, Cin), 53))
+    src = _bf(randn((B, 8, HW, Cout), 54))
+    sd, rd = skip.to(dev, torch.bfloat16), src.to(dev, torch.bfloat16)
+    dst = torch.empty_like(rd)
+    lib.sj_tc_launch_count(1)
+    _lib.check(lib.sj_res_add_fwd(sd.data_ptr(), rd.data_ptr(), dst.data_ptr(), C.byref(lin), B, HW, Cin, Cout,
+                                  _lib.SJ_BF16, _stream()), "res_add")
+    torch.cuda.synchronize()
+    assert lib.sj_tc_launch_count(1) == 1
+    weff = _bf(weights.collapse_conv3d_811(k))                       # [8,Cin,Cout], bf16-valued like the tc copy
+    ref = src + O.elu(torch.einsum("bnc,tcd->btnd", skip, weff) + b)
+    y = dst.float().cpu()
+    excess = (y - ref).abs() - (REL * ref.abs() + ABS)
+    assert excess.max().item() <= 0, f"res_add {Cin}->{Cout}: exceeds one output rounding by {excess.max().item():.3e}"
+    # in-place form used by the decoder (dst aliases src)
+    _lib.check(lib.sj_res_add_fwd(sd.data_ptr(), rd.data_ptr(), rd.data_ptr(), C.byref(lin), B, HW, Cin, Cout,
+                                  _lib.SJ_BF16, _stream()), "res_add in place")
+    torch.cuda.synchronize()
+    assert torch.equal(rd, dst)
