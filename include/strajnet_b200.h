@@ -16,10 +16,19 @@
  *   - `dtype` selects the activation type of `x`/`y`/intermediates (SJ_F32 or SJ_BF16);
  *     model inputs (rasters, actors) are always fp32; weights are fp32 ([in,out] Keras layout)
  *     with an optional bf16 tensor-core copy (`w_tc`, [out,in] K-major) used when dtype==SJ_BF16;
- *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state that results depend on
- *     (the launch-mode mask of sj_set_pdl and the per-thread timing probe are the only knobs, both opt-in);
+ *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state that results depend on;
  *     the caller owns all buffers including `workspace`; safe to capture in a CUDA graph;
  *   - return 0 (SJ_OK) or a negative SjStatus; never throws.
+ *
+ * Process-level knobs (none of them changes a result beyond the documented bf16 tolerance; all are opt-in):
+ *   - sj_set_pdl / SJ_PDL_MASK: programmatic dependent launch, OFF by default;
+ *   - sj_probe_start / sj_probe_stop: per-thread timing probe for bench.py;
+ *   - environment switches read once at first use, kept so that an earlier kernel generation can be re-measured against
+ *     its replacement (each selects between two implementations of the same op): SJ_DISABLE_FUSED_WMSA,
+ *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION,
+ *     SJ_DISABLE_ATTN_MMA, SJ_DISABLE_IM2COL_STAGED, SJ_DISABLE_NORM_FAST, SJ_DISABLE_FG_OFFSET_MMA (fall back to the
+ *     previous kernel), SJ_SIDE_STREAM (actor branch on a helper stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue
+ *     variants), SJ_NO_PDL (forces the PDL mask to 0).
  */
 #ifndef STRAJNET_B200_H_
 #define STRAJNET_B200_H_
@@ -159,8 +168,8 @@ const char* sj_last_cuda_error(void); /* text of the last CUDA failure seen by t
 long long sj_launch_count(int reset);
 /* of which tcgen05 (tensor-core) kernels */
 long long sj_tc_launch_count(int reset);
-/* Programmatic dependent launch (CUDA launch attribute "programmatic stream serialization"): when on (the default;
- * SJ_NO_PDL=1 in the environment turns it off), each kernel of a forward is launched so that its prologue overlaps
+/* Programmatic dependent launch (CUDA launch attribute "programmatic stream serialization"): OFF by default (inside a
+ * replayed CUDA graph it measured slower); when on, each kernel of a forward is launched so that its prologue overlaps
  * the tail of its predecessor on the stream; every kernel of the library orders itself behind its predecessor with
  * griddepcontrol.wait before touching activations, so results are identical either way.  `mask`: bit 0 = the
  * tcgen05 kernels, bit 1 = all other kernels (3 = every launch, 0 = off; SJ_PDL_MASK in the environment sets the
@@ -196,12 +205,6 @@ int sj_window_reverse_fwd(const void* windows, void* x, int B, int H, int W, int
 /* keras.layers.Dense(units=N, activation=act) as used throughout modules.py / trajNet.py: y = act(x[M,K] . w + b);
  * act 0 none, 1 tanh-GELU (modules.py:18), 2 ELU */
 int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K, int act, int dtype, sj_stream_t stream);
-
-/* Hardware-semantics probe (not part of the model path): y[m] = x[m + shift] . w_tc^T computed by pointing the
- * UMMA shared-memory descriptor `shift` rows (128 B each) into a 128B-swizzled TMA tile, with or without the
- * descriptor's base_offset field.  Documents whether shifted views of one staged tile are usable. */
-int sj_debug_gemm_shift(const void* x, void* y, const void* w_tc, int M, int N, int K, int shift, int use_base_offset,
-                        sj_stream_t stream);
 
 /* Mlp.call, modules.py:40-46: y = fc2(Gelu(fc1(x))), x [M,C] */
 size_t sj_mlp_workspace_bytes(int M, int C, int hidden, int dtype);
@@ -276,6 +279,13 @@ int sj_res_add_fwd(const void* skip, const void* src, void* dst, const SjLinear*
  * 2 = quantised submission bytes uint8 [B,256,256,32] (inference.py:124-136,160-182). */
 int sj_out_head_fwd(const void* x_occ, const void* x_flow, void* out, const SjDecoderW* w, int B, int out_layout,
                     int dtype, sj_stream_t stream);
+
+/* The decoder's tail: last up-sampling stage of both branches + both heads + final layout (modules.py:746-749 with
+ * i = 3, :732-737 second iteration, :767-770, :838): x3, f3 [B*8,128,128,96] -> out (out_layout as sj_out_head_fwd).
+ * With dtype == SJ_BF16 this is the fused path: the 48-channel full-resolution tensors stay on chip. */
+size_t sj_decoder_tail_workspace_bytes(int B, int dtype);
+int sj_decoder_tail_fwd(const void* x3, const void* f3, void* out, const SjDecoderW* w, int B, int out_layout, int dtype,
+                        void* workspace, size_t workspace_bytes, sj_stream_t stream);
 
 /* Raw I/O of the serving loop.  Inputs as the reference's record decode holds them before the
  * float casts (inference.py:91-93): ogm bool bytes [B,S,S,11,2] (SJ_IN_U8: nonzero -> 1.0), map int8 [B,256,256,3]

@@ -105,7 +105,6 @@ SIGNATURES = {
     "sj_window_partition_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sj_window_reverse_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sj_dense_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
-    "sj_debug_gemm_shift": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sj_mlp_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sj_mlp_fwd": (_i, [_p, _p, C.POINTER(SjLinear), C.POINTER(SjLinear), _i, _i, _i, _i, _p, _sz, _p]),
     "sj_window_attention_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -128,6 +127,8 @@ SIGNATURES = {
     "sj_upconv_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
     "sj_res_add_fwd": (_i, [_p, _p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
     "sj_out_head_fwd": (_i, [_p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p]),
+    "sj_decoder_tail_workspace_bytes": (_sz, [_i, _i]),
+    "sj_decoder_tail_fwd": (_i, [_p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_workspace_bytes": (_sz, [_i, _i, _i]),
     "sj_strajnet_fwd_io": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), C.POINTER(SjIoSpec), _i, _i, _i, _p, _sz, _p]),
     "sj_strajnet_fwd": (_i, [_p, _p, _p, _p, _p, _p, C.POINTER(SjModelW), _i, _i, _i, _p, _sz, _p]),

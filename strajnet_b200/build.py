@@ -16,6 +16,8 @@ OUT = os.path.join(OUT_DIR, "libstrajnet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("SJ_DEBUG_PROBES"):  # exports sj_debug_gemm_shift (tools/probe_shift.py); not in the product build
+    FLAGS.append("-DSJ_DEBUG_PROBES")
 
 
 def sources():

@@ -502,6 +502,33 @@ void res_add(Ctx& c, const void* skip, const SjLinear& w, const void* src, void*
   gemm(c, g);
 }
 
+// Last stage of both branches + the two heads (modules.py:746-749 with i = 3, :732-737 second iteration, :767-770, :838):
+// x3, f3 [B*8,128,128,96] -> out.  bf16: the 96 -> 48 up-convolutions are fused with the heads' channel contraction
+// (tc_upconv4h: x4 / f4 never reach HBM), head_tapsum finishes the 3x3 sums; otherwise up-convolution, then out_conv.
+void decoder_tail_impl(Ctx& c, const void* x3, const void* f3, void* out, const SjDecoderW& w, int B, int out_layout) {
+  const int NB = B * 8;
+  size_t mark = c.ws.mark();
+  static const bool fuse_off = getenv("SJ_DISABLE_HEAD_FUSION") != nullptr;
+  if (c.dtype == SJ_BF16 && w.out_w_tc && w.upconv[3].w_tc && w.upconv_f[1].w_tc && !fuse_off &&
+      tc_upconv4h_supported(128, 128, 96, 48)) {
+    void* zo = c.alloc((size_t)NB * 256 * 256 * 18 * 2);
+    void* zf = c.alloc((size_t)NB * 256 * 256 * 18 * 2);
+    const char* hw = (const char*)w.out_w_tc;
+    { RoleScope r(c, "dec.upconv3"); tc_upconv4h(c, x3, zo, w.upconv[3].w_tc, w.upconv[3].b, hw, NB, 128, 128); }
+    { RoleScope r(c, "dec.upconvf1"); tc_upconv4h(c, f3, zf, w.upconv_f[1].w_tc, w.upconv_f[1].b, hw + 32 * 64 * 2, NB, 128, 128); }
+    { RoleScope r(c, "dec.outconv"); head_tapsum(c, zo, zf, w.out_b, B, out_layout, out); }
+  } else {
+    void* x4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
+    void* f4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
+    { RoleScope r(c, "dec.upconv3"); upconv(c, x3, x4, w.upconv[3], NB, 128, 96, 48); }
+    { RoleScope r(c, "dec.upconvf1"); upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48); }
+    RoleScope r(c, "dec.outconv");
+    if (c.dtype == SJ_BF16 && w.out_w_tc) tc_out_conv(c, x4, f4, w.out_w_tc, w.out_b, B, out_layout, out);
+    else out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out);
+  }
+  c.ws.release(mark);
+}
+
 void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0, const void* res1, void* out,
                   const SjDecoderW& w, int B, int out_layout) {
   const int NB = B * 8;
@@ -510,7 +537,7 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
   void* x2 = c.alloc_act((size_t)NB * 64 * 64 * 128);
   void* fx = c.alloc_act((size_t)NB * 64 * 64 * 128);
   void* x3 = c.alloc_act((size_t)NB * 128 * 128 * 96);
-  void* x4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
+  void* f3 = c.alloc_act((size_t)NB * 128 * 128 * 96);
   { RoleScope r(c, "dec.upconv0"); upconv(c, x, x1, w.upconv[0], NB, 16, 384, 192); }
   { RoleScope r(c, "dec.res0"); res_add(c, res1, w.res[0], x1, x1, B, 32 * 32, 192, 192); }
   { RoleScope r(c, "dec.upconv1"); upconv(c, x1, x2, w.upconv[1], NB, 32, 192, 128); }
@@ -518,16 +545,8 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
   // uses x AFTER the res0 add (modules.py:762-765)
   { RoleScope r(c, "dec.resf"); res_add(c, flow_res, w.res_f, x2, fx, B, 64 * 64, 96, 128); }
   { RoleScope r(c, "dec.upconv2"); upconv(c, x2, x3, w.upconv[2], NB, 64, 128, 96); }
-  { RoleScope r(c, "dec.upconv3"); upconv(c, x3, x4, w.upconv[3], NB, 128, 96, 48); }
-  void* f3 = x3;  // x3 is dead once x4 exists
   { RoleScope r(c, "dec.upconvf0"); upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96); }
-  void* f4 = c.alloc_act((size_t)NB * 256 * 256 * 48);
-  { RoleScope r(c, "dec.upconvf1"); upconv(c, f3, f4, w.upconv_f[1], NB, 128, 96, 48); }
-  {
-    RoleScope r(c, "dec.outconv");
-    if (c.dtype == SJ_BF16 && w.out_w_tc) tc_out_conv(c, x4, f4, w.out_w_tc, w.out_b, B, out_layout, out);
-    else out_conv(c, x4, f4, w.out_w, w.out_b, B, out_layout, out);
-  }
+  decoder_tail_impl(c, x3, f3, out, w, B, out_layout);
   c.ws.release(mark);
 }
 
@@ -783,6 +802,7 @@ int sj_dense_fwd(const void* x, void* y, const SjLinear* w, int M, int N, int K,
 }
 
 // ---- hardware probe ----
+#ifdef SJ_DEBUG_PROBES  // hardware-semantics probe (tools/probe_shift.py); not part of the product ABI
 int sj_debug_gemm_shift(const void* x, void* y, const void* w_tc, int M, int N, int K, int shift, int use_base_offset,
                         sj_stream_t stream) {
   SJ_REQUIRE(x && y && w_tc && M > 0 && shift >= 0 && shift < 128);
@@ -793,6 +813,7 @@ int sj_debug_gemm_shift(const void* x, void* y, const void* w_tc, int M, int N, 
     tc_gemm(c, t);
   });
 }
+#endif
 
 // ---- WindowAttention ----
 static void wattn_body(Ctx& c, const void* xw, void* y, const SjSwinBlockW* w, int B_, int C, int heads, const float* mask,
@@ -959,6 +980,16 @@ int sj_out_head_fwd(const void* x_occ, const void* x_flow, void* out, const SjDe
     if (c.dtype == SJ_BF16 && w->out_w_tc) tc_out_conv(c, x_occ, x_flow, w->out_w_tc, w->out_b, B, out_layout, out);
     else out_conv(c, x_occ, x_flow, w->out_w, w->out_b, B, out_layout, out);
   });
+}
+
+size_t sj_decoder_tail_workspace_bytes(int B, int dtype) {
+  SjDecoderW z{};
+  return measure(dtype, [&](Ctx& c) { decoder_tail_impl(c, nullptr, nullptr, nullptr, z, B, 1); });
+}
+int sj_decoder_tail_fwd(const void* x3, const void* f3, void* out, const SjDecoderW* w, int B, int out_layout, int dtype,
+                        void* workspace, size_t workspace_bytes, sj_stream_t stream) {
+  SJ_REQUIRE(x3 && f3 && out && w && w->out_w && w->out_b && B > 0 && out_layout >= 0 && out_layout <= 2);
+  return run(workspace, workspace_bytes, dtype, stream, [&](Ctx& c) { decoder_tail_impl(c, x3, f3, out, *w, B, out_layout); });
 }
 
 // ---- STrajNet ----

@@ -210,8 +210,7 @@ void launch_mha(Ctx& c, const MhaP& p) {
   dim3 grid(cdiv(p.Nq, block), p.heads, p.batch);
   size_t smem = (size_t)2 * p.Nk * DP * 4 + (FG ? (33 * 33 + 2 * p.Nk) * 4 : 0) + (size_t)p.Nk * 4;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mha_kernel<T, D, FG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+    if (!SJ_SMEM_LIMIT_OK((mha_kernel<T, D, FG>), smem)) { c.fail(SJ_ECUDA); return; }
   }
   SJ_LAUNCH(c, "mha_core", (mha_kernel<T, D, FG>), grid, block, smem, p);
 }

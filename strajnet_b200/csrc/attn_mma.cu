@@ -287,8 +287,7 @@ void launch_attn(Ctx& c, AttnP p, int grid_x, int grid_y) {
   else extra = (228 + 64) * 4;
   const size_t smem = kv + extra;
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(attn_mma_kernel<DP, KCH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
+    if (!SJ_SMEM_LIMIT_OK((attn_mma_kernel<DP, KCH, MODE>), (int)smem)) {
       c.fail(SJ_ECUDA);
       return;
     }

@@ -77,7 +77,8 @@ void probe_after(Ctx& c, int slot);
 // memory another kernel of the forward may have written (and before its first global write), and pdl_trigger() near
 // its top.  Launched with programmatic stream serialisation, kernel i+1 then gets its CTAs scheduled, barriers
 // initialised, TMEM allocated and constant weights staged while kernel i drains, instead of after its last CTA has
-// retired.  Both are no-ops for a kernel launched without the attribute (SJ_NO_PDL=1).
+// retired.  Both are no-ops for a kernel launched without the attribute, which is the default (opt in: sj_set_pdl /
+// SJ_PDL_MASK).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // which launches get the attribute: bit 0 = tcgen05 kernels ("tc_*"), bit 1 = all others
@@ -99,6 +100,21 @@ inline void launch_kernel(const char* what, cudaStream_t stream, dim3 grid, dim3
   cfg.numAttrs = (pdl_mask() & (is_tc ? 1 : 2)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);
 }
+
+// Raises a kernel's dynamic shared-memory limit on first use per (call site, host thread, device) instead of on every
+// launch; evaluates to true when the limit is in place.
+#define SJ_SMEM_LIMIT_OK(kernel, bytes)                                                                        \
+  ([&]() -> bool {                                                                                             \
+    static thread_local int sj_dev_done_ = -1;                                                                 \
+    static thread_local cudaError_t sj_err_ = cudaSuccess;                                                     \
+    int sj_dev_ = 0;                                                                                           \
+    if (cudaGetDevice(&sj_dev_) != cudaSuccess) return false;                                                  \
+    if (sj_dev_ != sj_dev_done_) {                                                                             \
+      sj_err_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));        \
+      sj_dev_done_ = sj_dev_;                                                                                  \
+    }                                                                                                          \
+    return sj_err_ == cudaSuccess;                                                                             \
+  }())
 
 #define SJ_LAUNCH(ctx, what, kernel, grid, block, smem, ...)                                   \
   do {                                                                                        \

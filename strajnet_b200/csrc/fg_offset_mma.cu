@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) fg_offset_mma_kernel(const bf16* __restri
 bool fg_offset_mma(Ctx& c, const void* q, int ldq, const SjFgmsaW* w, int B, float* off, float* pos) {
   if (c.dtype != SJ_BF16 || ldq % 8 || (reinterpret_cast<uintptr_t>(q) & 15)) return false;
   const size_t smem = (size_t)HALO_PIX * PS * 2 + (8 * 32 + 64) * 4;
-  if (cudaFuncSetAttribute(fg_offset_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((fg_offset_mma_kernel), (int)smem)) {
     c.fail(SJ_ECUDA);
     return true;
   }

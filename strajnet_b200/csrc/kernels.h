@@ -222,6 +222,14 @@ void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* 
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,
                  int out_layout, void* out);
 
+// fused last up-convolution + head projection (tc_upconv4h.cu): x bf16 [NB,H,W,96] -> z fp16 [NB,2H,2W,18] with
+// z[q, tap*2+o] = sum_c ELU(upconv(x))[q,c] * head_w[tap,c,o]; head_w_tc = one head of SjDecoderW.out_w_tc
+bool tc_upconv4h_supported(int H, int W, int Cin, int Cout);
+void tc_upconv4h(Ctx& c, const void* x, void* z, const void* w_tc, const float* bias, const void* head_w_tc, int NB, int H,
+                 int W);
+// 9-tap shifted sum of both heads' projected columns + bias + final layout (headsum.cu); out_layout as out_conv
+void head_tapsum(Ctx& c, const void* z_occ, const void* z_flow, const float* bias, int B, int out_layout, void* out);
+
 // ---- validation-side loss / metrics (eval.cu) ----------------------------------------------------
 size_t eval_workspace_bytes();
 void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,

@@ -760,10 +760,10 @@ void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, con
   dim3 grid(256 / OC_TX, 256 / OC_TY, B);
   const size_t smem = (size_t)(OC_TY + 2) * (OC_TX + 2) * OC_PSTRIDE * c.esize() + 864 * sizeof(float2);
   if (c.dtype == SJ_BF16) {
-    if (cudaFuncSetAttribute(out_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+    if (!SJ_SMEM_LIMIT_OK((out_conv_kernel<bf16>), (int)smem)) { c.fail(SJ_ECUDA); return; }
     SJ_LAUNCH(c, "out_conv", out_conv_kernel<bf16>, grid, 128, smem, (const bf16*)x_occ, (const bf16*)x_flow, w, b, out_layout, out);
   } else {
-    if (cudaFuncSetAttribute(out_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+    if (!SJ_SMEM_LIMIT_OK((out_conv_kernel<float>), (int)smem)) { c.fail(SJ_ECUDA); return; }
     SJ_LAUNCH(c, "out_conv", out_conv_kernel<float>, grid, 128, smem, (const float*)x_occ, (const float*)x_flow, w, b, out_layout, out);
   }
 }

@@ -328,7 +328,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 2048;  // barriers + bias
   if (smem > 227 * 1024) { c.fail(SJ_EUNSUPPORTED); return; }
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
-  if (cudaFuncSetAttribute(tc_upconv_kernel<KC, NCH, RESB, A128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((tc_upconv_kernel<KC, NCH, RESB, A128>), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }

@@ -481,8 +481,7 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   const bool ln = a.ln_mean != nullptr;
 #define SJ_TCG2(ACT_, LN_, RPF_, EW_)                                                                                 \
   do {                                                                                                                \
-    if (cudaFuncSetAttribute(tc_gemm_kernel<ACT_, LN_, RPF_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                             227 * 1024) != cudaSuccess) {                                                            \
+    if (!SJ_SMEM_LIMIT_OK((tc_gemm_kernel<ACT_, LN_, RPF_, EW_>), 227 * 1024)) {                                                            \
       c.fail(SJ_ECUDA);                                                                                               \
       return;                                                                                                         \
     }                                                                                                                 \

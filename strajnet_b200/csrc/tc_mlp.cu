@@ -320,7 +320,7 @@ void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* 
   p.x = (const bf16*)x; p.out = (bf16*)out; p.mean = mean; p.rstd = rstd;
   p.colsum = w.fc1.tc_colsum; p.bias1 = w.fc1.tc_bias; p.bias2 = w.fc2.b;
   p.st_mean = st_mean; p.st_rstd = st_rstd;
-  if (cudaFuncSetAttribute(tc_mlp96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((tc_mlp96_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }

@@ -225,7 +225,7 @@ void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc
   OutP p{};
   p.B = B; p.num_tiles = B * (256 / TW) * (256 / TH); p.out_layout = out_layout; p.bias = bias; p.out = out;
   const size_t smem = 1024 + SMEM_BYTES;
-  if (cudaFuncSetAttribute(tc_outconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((tc_outconv_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }

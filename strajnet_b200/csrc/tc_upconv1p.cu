@@ -213,7 +213,7 @@ void tc_upconv1p(Ctx& c, const void* x, void* y, const void* w_tc, const float* 
     return;
   }
   const size_t smem = 1024 + SMEM_BYTES;
-  if (cudaFuncSetAttribute(tc_upconv1p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((tc_upconv1p_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }

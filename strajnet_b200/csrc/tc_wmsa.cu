@@ -401,7 +401,7 @@ void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* r
   p.mean2 = mean2; p.rstd2 = rstd2;
   p.colsum = w.qkv_ln.tc_colsum; p.biasf = w.qkv_ln.tc_bias; p.table = w.rpb_table; p.bproj = w.proj.b;
   const size_t smem = 1024 + SMEM_BYTES;
-  if (cudaFuncSetAttribute(tc_wmsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (!SJ_SMEM_LIMIT_OK((tc_wmsa_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }

@@ -31,6 +31,21 @@ def _inference_only(training) -> None:
         raise NotImplementedError("strajnet_b200 implements the inference path only: call with training=False")
 
 
+class OutputGrid(torch.Tensor):
+    """What `STrajNet.__call__` returns: the logits as a (CUDA) tensor that also answers the NumPy-side calls the
+    reference's serving loop makes on the model output and on slices of it -- `x[:, :, :, a:b]` (inference.py:109-113),
+    `.numpy()` (inference.py:169,175,181) and `np.asarray(x)` / `tf.convert_to_tensor(x)` through `__array__`
+    (`tf.sigmoid(x)`, inference.py:130) -- so that loop runs with only its import line edited.  Every torch operation on
+    it, slicing included, yields an OutputGrid again; `.numpy()` / `__array__` copy to the host on demand."""
+
+    def numpy(self, *args, **kwargs):
+        return self.detach().as_subclass(torch.Tensor).cpu().numpy(*args, **kwargs)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
 class Layer:
     """Minimal Keras-like layer: weights in Keras layout by attribute path, lazy `build()`."""
 
@@ -705,4 +720,4 @@ class STrajNet(Layer):
         obs = self._f32(obs, (48, 11, 8))
         occ = self._f32(occ, (16, 11, 8))  # mapt is ignored (actor_only=True, modules.py:778)
         out = torch.empty(ogm.shape[0], 256, 256, 32, dtype=torch.float32, device=self.device)
-        return self.forward_into(out, ogm, map_img, obs, occ, flow)
+        return self.forward_into(out, ogm, map_img, obs, occ, flow).as_subclass(OutputGrid)

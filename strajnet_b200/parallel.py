@@ -47,7 +47,10 @@ class DataParallelSTrajNet:
     def __init__(self, model, group=None):
         self.model, self.group = model, group
 
-    def __call__(self, ogm, map_img, training=True, obs=None, occ=None, mapt=None, flow=None):
+    def __call__(self, ogm, map_img, training=False, obs=None, occ=None, mapt=None, flow=None):
+        # inference-only wrapper: `training` defaults to False here (the model raises on True)
+        if obs is None or occ is None or flow is None:
+            raise ValueError("DataParallelSTrajNet: obs, occ and flow are required")
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         sh = shard_inputs(dict(ogm=ogm, map_img=map_img, obs=obs, occ=occ, flow=flow), rank, world)
@@ -142,28 +145,42 @@ class NcclAllGather:
 
 def make_gatherer(shard_shape, dtype, device, group=None, slots: int = 2, prefer_copy_engine: bool = True):
     """Collective constructor: the copy-engine gatherer when EVERY rank can build it and it reproduces the NCCL result
-    on a rank-stamped pattern, else the NCCL one.  SJ_GATHER=nccl forces the fallback."""
+    on a rank- and position-dependent pattern, else the NCCL one.  SJ_GATHER=nccl forces the fallback."""
     import os
     dev = torch.device(device)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     want = prefer_copy_engine and dev.type == "cuda" and world > 1 and os.environ.get("SJ_GATHER", "") != "nccl"
     if not want:
         return NcclAllGather(shard_shape, dtype, device, group, slots)
+    # symm.rendezvous is collective: agree that every rank can get that far BEFORE any rank enters it, so that a rank
+    # which cannot (module missing, no peer access) sends everybody to the NCCL path instead of leaving them hanging
     ag, ok = None, 1
+    try:
+        import torch.distributed._symmetric_memory as symm  # noqa: F401
+        if not all(torch.cuda.can_device_access_peer(dev.index, d) for d in range(torch.cuda.device_count()) if d != dev.index):
+            ok = 0
+    except Exception:  # noqa: BLE001
+        ok = 0
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        return NcclAllGather(shard_shape, dtype, device, group, slots)
     try:
         ag = PeerAllGather(shard_shape, dtype, dev, group, slots)
     except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL"
         import warnings
         warnings.warn(f"copy-engine all-gather unavailable on rank {dist.get_rank(group)}: {e}")
         ok = 0
-    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    flag.fill_(ok)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     if int(flag.item()) == 1:
         # self-check on every slot: shard = rank stamp, gathered result must equal the NCCL gather of the same shards
         rank = dist.get_rank(group)
         try:
             for s in range(slots):
-                ag.shard(s).fill_(float(rank + 1 + 10 * s))
+                # position-dependent pattern (a constant stamp cannot see an offset / stride error inside a shard)
+                pat = torch.arange(ag.shard(s).numel(), device=dev, dtype=torch.float32).remainder_(8191.0)
+                ag.shard(s).copy_((pat * (rank + 1) + 10 * s).reshape(ag.shard(s).shape).to(ag.shard(s).dtype))
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 ag.gather(s, ev).synchronize()

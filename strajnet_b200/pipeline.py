@@ -18,13 +18,18 @@ _KEYS = ("ogm", "map_img", "obs", "occ", "flow")
 
 
 class Handle:
-    def __init__(self, event: torch.cuda.Event, host_out: torch.Tensor):
-        self._event, self._out = event, host_out
+    def __init__(self, pipe: "InferencePipeline", slot: int, generation: int, event: torch.cuda.Event):
+        self._pipe, self._slot, self._gen, self._event = pipe, slot, generation, event
 
     def result(self) -> torch.Tensor:
-        """Block until this batch's logits are in host memory and return them (valid until the slot is reused)."""
+        """Block until this batch's logits are in host memory and return them (valid until the slot is reused).
+        Raises if the slot has already been handed to a later batch: the pinned buffer then holds (or is being
+        overwritten with) that batch's data."""
+        if self._pipe._generation[self._slot] != self._gen:
+            raise RuntimeError("InferencePipeline: this handle's slot was reused by a later submit(); consume results "
+                               f"within {self._pipe.depth} submits")
         self._event.synchronize()
-        return self._out
+        return self._pipe.host_out[self._slot]
 
 
 class InferencePipeline:
@@ -50,6 +55,7 @@ class InferencePipeline:
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]      # forward of slot done (inputs reusable)
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # logits of slot in host memory
+        self._generation = [0] * depth                                # submits seen per slot (stale-handle check)
         self.i = 0
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.dev_in[0].values())
         self.d2h_bytes = self.dev_out[0].numel() * self.dev_out[0].element_size()
@@ -83,8 +89,11 @@ class InferencePipeline:
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[s])
             self.host_out[s].copy_(self.dev_out[s], non_blocking=True)
-            self.ev_out[s].record(self.s_out)
-        return Handle(self.ev_out[s], self.host_out[s])
+            ev = torch.cuda.Event()  # a fresh event per submit: a stale handle never waits on a later batch's copy
+            ev.record(self.s_out)
+            self.ev_out[s] = ev
+        self._generation[s] += 1
+        return Handle(self, s, self._generation[s], ev)
 
     def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[Handle]:
         """Submit every batch, yielding the handle of batch i once batch i+depth-1 has been enqueued."""

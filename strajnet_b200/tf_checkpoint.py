@@ -15,8 +15,9 @@ module restates the published formats those files are made of, so trained weight
   attribute paths of SURVEY App. B (`encoder.basic_layers.0.blocks.1.attn.qkv.kernel`) are walked from the root.
 
 **Parity unpinned**: TensorFlow is not installable in this environment, so no TF-written checkpoint was available to
-read; the reader is tested against files produced by the writer below (same format description) and against the
-format's known constants (magic, CRC-32C vectors).
+read; the reader is tested against files produced by the writer below (same format description), against the format's
+known constants (magic, CRC-32C vectors) and against byte vectors assembled by hand from TensorFlow's published rules
+(the DT_STRING checksum of `WriteStringTensor`: lengths as fixed-width integers, then the length checksum, then bytes).
 """
 from __future__ import annotations
 
@@ -41,6 +42,22 @@ _DTYPE_CODE = {np.dtype(v): k for k, v in DTYPES.items()}
 
 def _mask(c: int) -> int:
     return ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + _MASK_DELTA) & 0xFFFFFFFF
+
+
+def string_tensor_crc(values: List[bytes]) -> Tuple[int, int]:
+    """Checksums of a DT_STRING tensor as TensorFlow's `WriteStringTensor` / `ReadStringTensor` compute them
+    (tensorflow/core/util/tensor_bundle/tensor_bundle.cc): the running CRC-32C covers every element LENGTH as a
+    fixed-width little-endian integer (uint32, or uint64 when it exceeds UINT32_MAX) -- not the varint bytes on disk --
+    then the 4 bytes of the masked length checksum, then all string bytes.  Returns (masked length checksum stored
+    after the varints, masked total stored in BundleEntryProto.crc32c)."""
+    c = 0
+    for v in values:
+        c = crc32c(struct.pack("<I", len(v)) if len(v) <= 0xFFFFFFFF else struct.pack("<Q", len(v)), c)
+    len_cksum = _mask(c)
+    c = crc32c(struct.pack("<I", len_cksum), c)
+    for v in values:
+        c = crc32c(v, c)
+    return len_cksum, _mask(c)
 
 
 # ------------------------------------------------------------------------------------------------ SSTable
@@ -179,7 +196,9 @@ class TensorBundle:
         raw = self._shards[s][e["offset"]:e["offset"] + e["size"]]
         if len(raw) != e["size"]:
             raise ValueError("data shard shorter than the index says")
-        if self.verify and e["crc"] is not None and _mask(crc32c(np.ascontiguousarray(raw))) != e["crc"]:
+        # DT_STRING entries carry a different checksum (string_tensor_crc): verified in read()
+        if (self.verify and e["crc"] is not None and e["dtype"] != DT_STRING
+                and _mask(crc32c(np.ascontiguousarray(raw))) != e["crc"]):
             raise ValueError("tensor checksum mismatch")
         return memoryview(np.ascontiguousarray(raw))
 
@@ -193,11 +212,16 @@ class TensorBundle:
             for _ in range(n):
                 ln, pos = _varint(raw, pos)
                 lens.append(ln)
-            pos += 4  # masked crc32c of the length varints
+            (len_cksum,) = struct.unpack("<I", raw[pos:pos + 4])
+            pos += 4
             vals = []
             for ln in lens:
                 vals.append(bytes(raw[pos:pos + ln]))
                 pos += ln
+            if self.verify:
+                want_len, want_all = string_tensor_crc(vals)
+                if len_cksum != want_len or (e["crc"] is not None and e["crc"] != want_all):
+                    raise ValueError("string tensor checksum mismatch")
             return vals[0] if not e["shape"] else vals
         if e["dtype"] == DT_BFLOAT16:
             a = np.frombuffer(raw, dtype="<u2").astype(np.uint32) << 16
@@ -294,12 +318,12 @@ def save_keras_checkpoint(prefix: str, weights: Dict[str, np.ndarray]) -> None:
     items: Dict[bytes, bytes] = {}
     data = bytearray()
 
-    def add_entry(key: str, dtype_code: int, shape, payload: bytes):
+    def add_entry(key: str, dtype_code: int, shape, payload: bytes, crc: Optional[int] = None):
         shape_msg = b"".join(_enc_ld(2, _enc_varint((1 << 3) | 0) + _enc_varint(int(d))) for d in shape)
         e = (_enc_varint((1 << 3) | 0) + _enc_varint(dtype_code) + _enc_ld(2, shape_msg) +
              (_enc_varint((4 << 3) | 0) + _enc_varint(len(data)) if len(data) else b"") +
              _enc_varint((5 << 3) | 0) + _enc_varint(len(payload)) +
-             _enc_varint((6 << 3) | 5) + struct.pack("<I", _mask(crc32c(payload))))
+             _enc_varint((6 << 3) | 5) + struct.pack("<I", _mask(crc32c(payload)) if crc is None else crc))
         items[key.encode("utf-8")] = e
         data.extend(payload)
 
@@ -315,8 +339,8 @@ def save_keras_checkpoint(prefix: str, weights: Dict[str, np.ndarray]) -> None:
         if nd["key"]:
             msg += _enc_ld(2, _enc_ld(1, b"VARIABLE_VALUE") + _enc_ld(3, nd["key"].encode("utf-8")))
         graph += _enc_ld(1, msg)
-    lens = _enc_varint(len(graph))
-    add_entry(OBJECT_GRAPH_KEY, DT_STRING, (), lens + struct.pack("<I", _mask(crc32c(lens))) + graph)
+    len_cksum, total = string_tensor_crc([graph])
+    add_entry(OBJECT_GRAPH_KEY, DT_STRING, (), _enc_varint(len(graph)) + struct.pack("<I", len_cksum) + graph, crc=total)
     items[b""] = _enc_varint((1 << 3) | 0) + _enc_varint(1) + _enc_ld(3, _enc_varint((1 << 3) | 0) + _enc_varint(1))
     write_table(prefix + ".index", items)
     open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))

@@ -73,17 +73,40 @@ def test_bfloat16_and_string_entries(tmp_path):
     bf = (vals.view(np.uint32) >> 16).astype("<u2").tobytes()
     strs = [b"ab", b"", b"xyz"]
     lens = b"".join(_enc_varint(len(s)) for s in strs)
-    sp = lens + struct.pack("<I", T._mask(crc32c(lens))) + b"".join(strs)
+    # TensorFlow's WriteStringTensor rule, spelled out (NOT through the module's helper): the CRC runs over each length
+    # as a fixed-width uint32, then over the 4 bytes of the masked length checksum, then over the string bytes
+    c = 0
+    for s_ in strs:
+        c = crc32c(struct.pack("<I", len(s_)), c)
+    len_ck = T._mask(c)
+    c = crc32c(struct.pack("<I", len_ck), c)
+    c = crc32c(b"".join(strs), c)
+    str_crc = T._mask(c)
+    sp = lens + struct.pack("<I", len_ck) + b"".join(strs)
 
-    def entry(dtype, shape, off, payload):
+    def entry(dtype, shape, off, payload, crc=None):
         sm = b"".join(_enc_ld(2, _enc_varint(8) + _enc_varint(d)) for d in shape)
         return (_enc_varint(8) + _enc_varint(dtype) + _enc_ld(2, sm) + (_enc_varint(32) + _enc_varint(off) if off else b"") +
-                _enc_varint(40) + _enc_varint(len(payload)) + _enc_varint(53) + struct.pack("<I", T._mask(crc32c(payload))))
+                _enc_varint(40) + _enc_varint(len(payload)) + _enc_varint(53) +
+                struct.pack("<I", T._mask(crc32c(payload)) if crc is None else crc))
 
-    T.write_table(prefix + ".index", {b"": _enc_varint(8) + _enc_varint(1), b"h": entry(14, [3], 0, bf), b"s": entry(7, [3], len(bf), sp)})
-    open(prefix + ".data-00000-of-00001", "wb").write(bf + sp)
+    def write(string_entry_crc, string_payload):
+        T.write_table(prefix + ".index", {b"": _enc_varint(8) + _enc_varint(1), b"h": entry(14, [3], 0, bf),
+                                          b"s": entry(7, [3], len(bf), string_payload, string_entry_crc)})
+        open(prefix + ".data-00000-of-00001", "wb").write(bf + string_payload)
+
+    write(str_crc, sp)
     b = T.TensorBundle(prefix)
     assert np.array_equal(b.read("h"), vals) and b.read("s") == strs
+    assert T.string_tensor_crc(strs) == (len_ck, str_crc)
+    # the checksum over the raw on-disk bytes (varint lengths included) is NOT what TensorFlow stores: must be rejected
+    write(T._mask(crc32c(sp)), sp)
+    with pytest.raises(ValueError):
+        T.TensorBundle(prefix).read("s")
+    # ... and so must a wrong length checksum
+    write(str_crc, lens + struct.pack("<I", T._mask(crc32c(lens))) + b"".join(strs))
+    with pytest.raises(ValueError):
+        T.TensorBundle(prefix).read("s")
 
 
 def test_object_graph_skips_keras_aliases(tmp_path):

@@ -1,7 +1,12 @@
+"""Needs a library built with SJ_DEBUG_PROBES=1 (`SJ_DEBUG_PROBES=1 python -m strajnet_b200.build --force`): the probe entry
+point sj_debug_gemm_shift is not part of the product ABI."""
 import sys, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from strajnet_b200 import _lib
 L = _lib.lib()
+import ctypes as C
+L.sj_debug_gemm_shift.restype = C.c_int
+L.sj_debug_gemm_shift.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]
 torch.manual_seed(0)
 M, N, K = 384, 64, 128
 x = torch.randn(M + 256, K, device='cuda').to(torch.bfloat16)
