@@ -34,10 +34,13 @@ class Handle:
 
 class InferencePipeline:
     def __init__(self, model, batch: int, depth: int = 2, raw_inputs: bool = False, quantized: bool = False,
-                 graph: bool = True):
+                 graph: bool = True, gather: bool = False, group=None):
         """raw_inputs: ogm arrives as uint8/bool and map_img as int8 (the record's own types, inference.py:91-93);
         quantized: results are the uint8 submission bytes (inference.py:160-182) instead of fp32 logits;
-        graph: replay one captured CUDA graph per device slot instead of ~90 stream launches per step."""
+        graph: replay one captured CUDA graph per device slot instead of ~90 stream launches per step;
+        gather (data-parallel serving, one process per GPU): every step's result grids are all-gathered on every rank
+        (`gathered(slot)`), by `parallel.make_gatherer` on its own stream -- copy engines over NVLink peer memory when
+        available, so no SM and no host thread is taken from the forwards; collective: construct on every rank."""
         self.model, self.B, self.depth, self.graph = model, batch, depth, graph
         dev = model.device
         S = model.cfg["input_size"][0]
@@ -49,7 +52,15 @@ class InferencePipeline:
         odt = torch.uint8 if quantized else torch.float32
         self.dev_in: List[Dict[str, torch.Tensor]] = [
             {k: torch.empty(shapes[k], dtype=dts[k], device=dev) for k in _KEYS} for _ in range(depth)]
-        self.dev_out = [torch.empty(batch, 256, 256, 32, dtype=odt, device=dev) for _ in range(depth)]
+        self.gatherer, self.gather_kind = None, "none"
+        if gather:
+            from .parallel import make_gatherer
+            self.gatherer = make_gatherer((batch, 256, 256, 32), odt, dev, group=group, slots=depth)
+            self.gather_kind = self.gatherer.kind
+            self.dev_out = [self.gatherer.shard(s) for s in range(depth)]  # the forward writes straight into the shard
+        else:
+            self.dev_out = [torch.empty(batch, 256, 256, 32, dtype=odt, device=dev) for _ in range(depth)]
+        self.ev_gathered = [None] * depth
         self.host_out = [torch.empty(batch, 256, 256, 32, dtype=odt).pin_memory() for _ in range(depth)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
@@ -82,10 +93,14 @@ class InferencePipeline:
             self.s_run.wait_event(self.ev_in[s])
             if not first_use:
                 self.s_run.wait_event(self.ev_out[s])  # the previous logits of this slot have left the device
+                if self.ev_gathered[s] is not None:
+                    self.s_run.wait_event(self.ev_gathered[s])  # ... and every rank has pulled the shard
             d = self.dev_in[s]
             # fixed device slots: the forward of each slot is a replayed CUDA graph after its first use
             self.model.forward_into(self.dev_out[s], d["ogm"], d["map_img"], d["obs"], d["occ"], d["flow"], graph=self.graph)
             self.ev_run[s].record(self.s_run)
+        if self.gatherer is not None:
+            self.ev_gathered[s] = self.gatherer.gather(s, self.ev_run[s])
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[s])
             self.host_out[s].copy_(self.dev_out[s], non_blocking=True)
@@ -104,6 +119,16 @@ class InferencePipeline:
                 yield pending.pop(0)
         yield from pending
 
+    def gathered(self, slot: int) -> torch.Tensor:
+        """[world * B, 256, 256, 32] grids of the batch last submitted to `slot` (valid once its gather event has fired)."""
+        if self.gatherer is None:
+            raise RuntimeError("InferencePipeline was built without gather=True")
+        if self.ev_gathered[slot] is not None:
+            self.ev_gathered[slot].synchronize()
+        return self.gatherer.full[slot]
+
     def synchronize(self) -> None:
         for s in (self.s_in, self.s_run, self.s_out):
             s.synchronize()
+        if self.gatherer is not None and self.gatherer.stream is not None:
+            self.gatherer.stream.synchronize()

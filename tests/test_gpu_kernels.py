@@ -239,3 +239,94 @@ def test_decoder_tail_fused_tight(env, mode):
         lo, hi = O.quantize_outputs(ref - tol).to(torch.int16), O.quantize_outputs(ref + tol).to(torch.int16)
         ok = (q == qr) | (q == lo) | (q == hi)
         assert ok.all(), f"{(~ok).sum().item()} quantised bytes differ beyond a {tol:.1e} logit perturbation"
+
+
+# ---- fused Swin kernels (K1 = tc_wmsa, fused MLP = tc_mlp96), isolated through SwinTransformerBlock -----------------
+def _ln_stats(x):
+    mu = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mu * mu
+    return mu, torch.rsqrt(var.clamp_min(0) + 1e-5)
+
+
+def _wmsa_emulated(x, w, H, heads, shift):
+    """x + proj(window_attention(norm1(x))) with the kernel's rounding points (tc_wmsa.cu): norm1 folded into the bf16
+    qkv weights (rstd*(x.W' - mean*colsum) + bias'), q/k/v rounded to bf16 (q pre-scaled by d^-0.5 log2 e), exp2-domain
+    softmax with bf16 un-normalised P and an fp32 row sum, O/sum rounded to bf16, bf16 proj weights."""
+    B, L, C = x.shape
+    d = C // heads
+    g, bt = w["norm1.gamma"], w["norm1.beta"]
+    wq = _bf(w["attn.qkv.kernel"] * g[:, None])                                 # [C,3C] folded, bf16-valued
+    colsum = wq.sum(0)
+    biasf = w["attn.qkv.bias"] + (bt[:, None].double() * w["attn.qkv.kernel"].double()).sum(0).float()
+    mu, rstd = _ln_stats(x)
+    qkv = rstd * (x @ wq - mu * colsum) + biasf                                  # [B,L,3C]
+    y = qkv.reshape(B, H, H, 3 * C)
+    if shift:
+        y = torch.roll(y, shifts=(-shift, -shift), dims=(1, 2))
+    yw = O.window_partition(y, 8).reshape(-1, 64, 3, heads, d).permute(2, 0, 3, 1, 4)   # [3, nWin, h, 64, d]
+    LOG2E = 1.4426950408889634
+    q, k, v = _bf(yw[0] * (d ** -0.5 * LOG2E)), _bf(yw[1]), _bf(yw[2])
+    s = q @ k.transpose(-1, -2)
+    idx = torch.from_numpy(O.relative_position_index(8).reshape(-1))
+    bias = w["attn.relative_position_bias_table"][idx].reshape(64, 64, heads).permute(2, 0, 1)
+    s = s + bias.unsqueeze(0) * LOG2E
+    if shift:
+        mask = torch.from_numpy(O.shift_attn_mask(H, H, 8, shift)).float()
+        nW = mask.shape[0]
+        s = (s.reshape(-1, nW, heads, 64, 64) + (mask * LOG2E)[None, :, None]).reshape(-1, heads, 64, 64)
+    p = torch.exp2(s - s.max(-1, keepdim=True).values)
+    o = _bf((_bf(p) @ v) / p.sum(-1, keepdim=True))                              # [nWin,h,64,d]
+    o = o.permute(0, 2, 1, 3).reshape(-1, 8, 8, C)
+    o = O.window_reverse(o, 8, H, H, C)
+    if shift:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    return x + o.reshape(B, L, C) @ _bf(w["attn.proj.kernel"]) + w["attn.proj.bias"]
+
+
+@pytest.mark.parametrize("shift", [0, 4])
+def test_tc_wmsa_tight(env, shift):
+    """K1 alone: fc2 is zeroed so that the block returns x1 = x + attention exactly (the fused MLP adds 0).  640 tiles."""
+    import strajnet_b200 as sj
+    _lib, _, _ = env
+    B, H, C, heads = 20, 64, 96, 3
+    w = O.make_block_weights(C, heads, seed=21)
+    w["mlp.fc2.kernel"] = torch.zeros_like(w["mlp.fc2.kernel"])
+    w["mlp.fc2.bias"] = torch.zeros_like(w["mlp.fc2.bias"])
+    blk = sj.SwinTransformerBlock(C, (H, H), heads, window_size=8, shift_size=shift, dtype="bfloat16")
+    blk.set_weights(w)
+    x = _bf(randn((B, H * H, C), 22))
+    _lib.lib().sj_tc_launch_count(1)
+    y = blk(x).float().cpu()
+    assert _lib.lib().sj_tc_launch_count(1) == 2, "fused window-MSA + fused MLP kernels expected"
+    ref = _wmsa_emulated(x, w, H, heads, shift)
+    err = (y - ref).abs()
+    tol = REL * ref.abs() + 4e-3   # one output rounding + rounding-tie flips of the bf16 q/k/v/P/O intermediates
+    print(f"tc_wmsa shift {shift}: max |err| {err.max().item():.3e}")
+    assert (err <= tol).all(), f"tc_wmsa shift {shift}: max excess {(err - tol).max().item():.3e}"
+    # against the plain fp32 oracle block: bf16 operand rounding only
+    lit = O.swin_block(x, w, "", H, H, heads, 8, shift)
+    assert (y - lit).abs().max().item() < 3e-2
+
+
+def test_tc_mlp96_tight(env):
+    """Fused MLP alone: proj is zeroed so that x1 = x.  norm2 folded into bf16 fc1, tanh-GELU, bf16 hidden, bf16 fc2."""
+    import strajnet_b200 as sj
+    _lib, _, _ = env
+    B, H, C, heads = 20, 64, 96, 3
+    w = O.make_block_weights(C, heads, seed=23)
+    w["attn.proj.kernel"] = torch.zeros_like(w["attn.proj.kernel"])
+    w["attn.proj.bias"] = torch.zeros_like(w["attn.proj.bias"])
+    blk = sj.SwinTransformerBlock(C, (H, H), heads, window_size=8, shift_size=0, dtype="bfloat16")
+    blk.set_weights(w)
+    x = _bf(randn((B, H * H, C), 24))
+    y = blk(x).float().cpu()
+    g, bt = w["norm2.gamma"], w["norm2.beta"]
+    w1 = _bf(w["mlp.fc1.kernel"] * g[:, None])
+    b1 = w["mlp.fc1.bias"] + (bt[:, None].double() * w["mlp.fc1.kernel"].double()).sum(0).float()
+    mu, rstd = _ln_stats(x)
+    h = _bf(O.gelu_tanh(rstd * (x @ w1 - mu * w1.sum(0)) + b1))
+    ref = x + h @ _bf(w["mlp.fc2.kernel"]) + w["mlp.fc2.bias"]
+    err = (y - ref).abs()
+    tol = REL * ref.abs() + 4e-3   # + tanh.approx (2^-11) through fc2 and rounding-tie flips of the bf16 hidden tile
+    print(f"tc_mlp96: max |err| {err.max().item():.3e}")
+    assert (err <= tol).all(), f"tc_mlp96: max excess {(err - tol).max().item():.3e}"

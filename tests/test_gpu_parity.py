@@ -467,3 +467,30 @@ def test_headline_batch16_bf16_batch_invariance(sj):
     for i in (0, 7, 15):
         one = {k: v[i:i + 1] for k, v in inp.items()}
         assert torch.equal(_fwd(m, one)[0], y[i]), f"sample {i} differs between batch 16 and batch 1"
+
+
+@pytest.mark.parametrize("name,B,S,large", [("config3_b2", 2, 256, False), ("config3_b16", 16, 256, False),
+                                             ("config5_b4", 4, 512, True)])
+def test_strajnet_bf16_error_profile(sj, name, B, S, large):
+    """The benchmarked arithmetic (bf16 tensor-core path) against the fp32 oracle at the benchmarked sizes, gated on the
+    error DISTRIBUTION rather than on the maximum alone: mean, 99.9th percentile, and the image border against the
+    interior (a wrong border tap of a sub-pixel phase or a mis-placed halo shows up as a border / interior gap long before
+    it moves the maximum of 2 M logits)."""
+    m = _model(sj, dtype="bfloat16", large=large)
+    inp = O.make_inputs(B, S, seed=31)
+    y = _fwd(m, inp).float().cpu()
+    ref = O.forward_from_inputs(oracle_model(), O.CFG512 if large else CFG256, inp, large_ogm=large)
+    err = (y - ref).abs()
+    rng = ref.abs().max().item()
+    flat = err.flatten()
+    p999 = flat.kthvalue(int(0.999 * flat.numel())).values.item()
+    border = torch.zeros(256, 256, dtype=torch.bool)
+    border[0, :] = border[-1, :] = border[:, 0] = border[:, -1] = True
+    rms_b = err[:, border].pow(2).mean().sqrt().item()
+    rms_i = err[:, ~border].pow(2).mean().sqrt().item()
+    print(f"bf16 {name}: max {flat.max().item():.3e} ({flat.max().item() / rng:.3%} of range {rng:.2f}), mean {flat.mean().item():.3e}, "
+          f"p99.9 {p999:.3e}, rms border {rms_b:.3e} / interior {rms_i:.3e}")
+    assert torch.isfinite(y).all()
+    assert flat.max().item() < 0.08 * rng
+    assert flat.mean().item() < 2.5e-2 and p999 < 0.1
+    assert rms_b < 1.6 * rms_i + 1e-3

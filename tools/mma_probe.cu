@@ -107,14 +107,20 @@ __device__ __forceinline__ void issue_step(uint32_t tmem, uint32_t a_lo, uint32_
 template <int PAT>
 constexpr int mmas_per_step() { return PAT == 0 || PAT == 4 ? 8 : (PAT == 1 ? 20 : (PAT == 2 ? 32 : 8)); }
 
+__device__ int g_random_data = 0;  // 1: operands = random bf16 bit patterns in [-2, 2] (tensor-core power as in real kernels)
 template <int PAT, int N, int RB, int TS, int CTA2>
 __device__ __forceinline__ void probe_body(int steps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u ^ ((i * 2654435761u) & 0x00700070u);
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
+    uint32_t h = (i + 1) * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // random: sign + mantissa random, exponent in {0x3e, 0x3f} (|x| in [0.125, 2)); constant-ish: ~0.0078 with 3 low bits varying
+    reinterpret_cast<uint32_t*>(smem)[i] = g_random_data ? ((h & 0x80ff80ffu) | 0x3e003e00u | ((h >> 3) & 0x01000100u))
+                                                         : (0x3c003c00u ^ ((i * 2654435761u) & 0x00700070u));
+  }
   const int warp = uniform_warp_idx();
   uint32_t rank = 0;
   if constexpr (CTA2) rank = cluster_ctarank();
@@ -313,6 +319,35 @@ int main(int argc, char** argv) {
            10 * run(probe2_kernel<1, 0, 64>, 20, true, 148));
     printf("cta_group::2, 16 MMAs of N = 48:  %7.1f\n", 16 * run(probe2_kernel<2, 0, 64>, 32, true, 2));
     printf("cta_group::2, 4 MMAs of N = 192:  %7.1f\n", 4 * run(probe2_kernel<3, 0, 64>, 8, true, 2));
+  }
+  if (on("power")) {
+    // steady-state cost under load: the 10-MMA pattern on all 148 SMs for ~10 ms per launch, 12 launches back to back,
+    // with near-constant operands (low toggle rate) and with random operands (what a real layer feeds the tensor cores)
+    auto kernel = probe1_kernel<1, 0, 64, 0>;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      CK(cudaMemcpyToSymbol(g_random_data, &rnd, sizeof(int)));
+      const int steps = 20000;
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        for (int l = 0; l < 12; ++l) kernel<<<148, 128, SMEM>>>(steps, d_out);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::vector<long long> h(148);
+        CK(cudaMemcpy(h.data(), d_out, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+        double cyc = 0;
+        for (int i = 0; i < 148; ++i) cyc += (double)h[i] / 148;
+        printf("%s operands: %.1f cycles per K16 slice (10 MMAs), last launch %.0f cycles, 12 launches in %.2f ms -> SM clock ~%.0f MHz\n",
+               rnd ? "random  " : "constant", cyc / (steps * 2.0), cyc, ms, cyc * 12 / (ms * 1e3));
+      }
+    }
+    int zero = 0;
+    CK(cudaMemcpyToSymbol(g_random_data, &zero, sizeof(int)));
   }
   // ---- TS functional check
   if (on("tscheck")) {
