@@ -22,7 +22,6 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
-#include <cstdlib>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -61,9 +60,6 @@ struct Up4hP {
   int NB, H, W, tiles_x, tiles_y, num_tiles;
   const float* bias;
   __half* z;  // [NB, 2H, 2W, 18]
-  long long* stats;  // optional [grid][8]: cycle accounting of the MMA warp (SJ_UP4H_DBG bit 32)
-  int dbg;    // ablation switches (SJ_UP4H_DBG, measurement only): 1 no conv MMAs, 2 no ELU / operand store, 4 no Z stores,
-              // 8 no Z read-out at all, 16 no projection MMAs
 };
 
 // D[tmem] (+)= A[tmem] . B[smem]^T: A = 128 lanes x 16 bf16 (8 packed 32-bit columns)
@@ -192,19 +188,13 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t idesc1 = make_idesc_bf16(128, COUT), idesc2 = make_idesc_bf16(128, 2 * COUT),
                    idesc4 = make_idesc_bf16(128, 4 * COUT), idesc_z = make_idesc_bf16(128, 32);
     const uint32_t b_lo = desc_lo(smem_u32(smem_b)), w2_lo = desc_lo(smem_u32(smem + OFF_W2));
-    long long st_te = 0, st_af = 0, st_a2 = 0, st_ze = 0;  // cycles waiting on tempty / afull / a2full / zempty
     // projection of local tile j (accumulator stage j & 1): A = the bf16 rows the epilogue stored over the accumulator
     auto project = [&](int j) {
       const int acc = j & 1;
-      long long w0 = clock64();
       mbar_wait(&a2full[acc], (uint32_t)(j >> 1) & 1);
-      long long w1 = clock64();
       mbar_wait(zempty, ((uint32_t)j & 1) ^ 1);  // Z of tile j-1 has been read out
-      st_a2 += w1 - w0;
-      st_ze += clock64() - w1;
       tc_fence_after();
       if (elect_one()) {
-        if (!(p.dbg & 16))
 #pragma unroll
         for (int ring = 0; ring < 4; ++ring)
 #pragma unroll
@@ -220,29 +210,17 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     uint32_t sph = 0;
     mbar_wait(bfull, 0);
     tc_fence_after();
-    const long long t_begin = clock64();
-    unsigned long long g_begin;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++j) {
       const int acc = j & 1;
-      {
-        long long w0 = clock64();
-        mbar_wait(&tempty[acc], ((uint32_t)(j >> 1) & 1) ^ 1);
-        st_te += clock64() - w0;
-      }
+      mbar_wait(&tempty[acc], ((uint32_t)(j >> 1) & 1) ^ 1);
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
-        {
-          long long w0 = clock64();
-          mbar_wait(&afull[slot], sph);
-          st_af += clock64() - w0;
-        }
+        mbar_wait(&afull[slot], sph);
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smem_u32(smem + slot * A_SUB));
         const uint32_t bc_lo = b_lo + ((ch * 16 * B_TILE) >> 4);
         if (elect_one()) {
-          if (!(p.dbg & 1))
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
 #pragma unroll
@@ -263,14 +241,6 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
     if (j > 0) project(j - 1);
-    if (p.stats && (p.dbg & 32) && lane == 0) {
-      mbar_wait(zfull, (uint32_t)(j - 1) & 1);  // last MMA of this CTA has completed
-      unsigned long long g_end;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
-      long long* o = p.stats + blockIdx.x * 8;
-      o[0] = clock64() - t_begin; o[1] = (long long)(g_end - g_begin); o[2] = j;
-      o[3] = st_te; o[4] = st_af; o[5] = st_a2; o[6] = st_ze;
-    }
   } else {
     const int quarter = warp % 4, py = (warp - 2) / 4, ew = warp - 2;
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
@@ -284,12 +254,6 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     auto read_out = [&](int jz, int tz) {
       mbar_wait(zfull, (uint32_t)jz & 1);
       tc_fence_after();
-      if (p.dbg & 8) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(zempty);
-        return;
-      }
       uint32_t zq[2][9];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -327,7 +291,6 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const int row = c / (STG_ROW / 16), col = c % (STG_ROW / 16);
           const uint4 v = *reinterpret_cast<const uint4*>(stg + row * STG_ROW + col * 16);
           const long long Y = 2 * (y0 + quarter * 4 + row) + py;
-          if (!(p.dbg & 4))
           *reinterpret_cast<uint4*>(zg + (((long long)n * (2 * p.H) + Y) * (2 * p.W) + 2 * x0) * (ZCH * 2) + col * 16) = v;
         }
       }
@@ -339,7 +302,6 @@ tc_upconv4h_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const int acc = j & 1;
       mbar_wait(&tfull[acc], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
-      if (!(p.dbg & 2))
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t t_addr = tmem_base + lane_addr + acc * ACC_COLS + (py * 2 + half) * COUT;
@@ -398,12 +360,6 @@ void tc_upconv4h(Ctx& c, const void* x, void* z, const void* w_tc, const float* 
   p.num_tiles = NB * p.tiles_x * p.tiles_y;
   p.bias = bias;
   p.z = (__half*)z;
-  static const int dbg = getenv("SJ_UP4H_DBG") ? atoi(getenv("SJ_UP4H_DBG")) : 0;
-  p.dbg = dbg;
-  static long long* stats = nullptr;  // measurement only (never in the product path: bit 32 is opt-in)
-  if ((dbg & 32) && !stats) cudaMalloc(&stats, 256 * 8 * sizeof(long long));
-  p.stats = stats;
-
   CUtensorMap mapA, mapB, mapW2;
   uint64_t da[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
   uint64_t sa[3] = {(uint64_t)CIN * 2, (uint64_t)W * CIN * 2, (uint64_t)H * W * CIN * 2};
@@ -424,20 +380,6 @@ void tc_upconv4h(Ctx& c, const void* x, void* z, const void* w_tc, const float* 
   if (!SJ_SMEM_LIMIT_OK(tc_upconv4h_kernel, 227 * 1024)) { c.fail(SJ_ECUDA); return; }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   SJ_LAUNCH(c, "tc_upconv4h", tc_upconv4h_kernel, grid, NTHREADS, smem, mapA, mapB, mapW2, p);
-  if ((dbg & 32) && stats) {  // measurement only: synchronises and prints the MMA warp's cycle accounting
-    static int printed = 0;
-    long long h[256 * 8];
-    if (cudaStreamSynchronize(c.stream) == cudaSuccess &&
-        cudaMemcpy(h, stats, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost) == cudaSuccess && ++printed > 6 && printed < 10) {
-      double s[8] = {0};
-      for (int i = 0; i < grid; ++i)
-        for (int k = 0; k < 8; ++k) s[k] += (double)h[i * 8 + k] / grid;
-      fprintf(stderr,
-              "up4h stats (mean over %d CTAs): %.0f cycles, %.1f us (clock %.0f MHz), %.1f tiles -> %.0f cycles/tile; waits per "
-              "tile: tempty %.0f afull %.0f a2full %.0f zempty %.0f\n",
-              grid, s[0], s[1] / 1e3, s[0] / s[1] * 1e3, s[2], s[0] / s[2], s[3] / s[2], s[4] / s[2], s[5] / s[2], s[6] / s[2]);
-    }
-  }
 }
 
 }  // namespace sj

@@ -107,12 +107,14 @@ __device__ __forceinline__ void issue_step(uint32_t tmem, uint32_t a_lo, uint32_
 template <int PAT>
 constexpr int mmas_per_step() { return PAT == 0 || PAT == 4 ? 8 : (PAT == 1 ? 20 : (PAT == 2 ? 32 : 8)); }
 
-__device__ int g_random_data = 0;  // 1: operands = random bf16 bit patterns in [-2, 2] (tensor-core power as in real kernels)
+__device__ int g_random_data = 0;
+__device__ int g_extras = 0;  // bit 0: tcgen05.commit after every step (20 MMAs of PAT 1); bit 1: + tcgen05.fence::after_thread_sync;
+                              // bit 2: + an mbarrier wait on that commit every 3rd step (the kernel's per-tile hand-off)  // 1: operands = random bf16 bit patterns in [-2, 2] (tensor-core power as in real kernels)
 template <int PAT, int N, int RB, int TS, int CTA2>
 __device__ __forceinline__ void probe_body(int steps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
     uint32_t h = (i + 1) * 2654435761u;
@@ -126,6 +128,7 @@ __device__ __forceinline__ void probe_body(int steps, long long* out) {
   if constexpr (CTA2) rank = cluster_ctarank();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -148,8 +151,25 @@ __device__ __forceinline__ void probe_body(int steps, long long* out) {
     const long long t0 = clock64();
     if (rank == 0) {
       if (elect_one()) {
+        const int extras = g_extras;
+        uint32_t xph = 0;
 #pragma unroll 1
-        for (int s = 0; s < steps; ++s) issue_step<PAT, N, RB, TS, CTA2>(tmem, a_lo, b_lo, s);
+        for (int s = 0; s < steps; ++s) {
+          issue_step<PAT, N, RB, TS, CTA2>(tmem, a_lo, b_lo, s);
+          if (extras & 1) {
+            if constexpr (!CTA2) umma_commit(&bar2);
+            if (extras & 2) tc_fence_after();
+            if ((extras & 4) && s % 3 == 2) {
+              // wait until everything issued so far has completed (phase parity of the commit just issued)
+              // each commit completes one phase of bar2 (count 1): the commit of step s completes phase s
+              uint32_t done = 0;
+              while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&bar2)), "r"((uint32_t)(s & 1)) : "memory");
+            }
+          }
+        }
+        (void)xph;
         if constexpr (CTA2)
           asm volatile(
               "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -319,6 +339,16 @@ int main(int argc, char** argv) {
            10 * run(probe2_kernel<1, 0, 64>, 20, true, 148));
     printf("cta_group::2, 16 MMAs of N = 48:  %7.1f\n", 16 * run(probe2_kernel<2, 0, 64>, 32, true, 2));
     printf("cta_group::2, 4 MMAs of N = 192:  %7.1f\n", 4 * run(probe2_kernel<3, 0, 64>, 8, true, 2));
+  }
+  if (on("commit")) {
+    printf("# cost of tcgen05.commit / fence / a full hand-off inside the 10-MMA pattern stream (cycles per K16 slice, floor 384, plain 515)\n");
+    for (int ex : {0, 1, 3, 5, 7}) {
+      CK(cudaMemcpyToSymbol(g_extras, &ex, sizeof(int)));
+      printf("extras=%d (%s%s%s): %7.1f\n", ex, ex & 1 ? "commit per 20 MMAs" : "none", ex & 2 ? " + fence" : "",
+             ex & 4 ? " + wait for completion every 60 MMAs" : "", 10 * run(probe1_kernel<1, 0, 64, 0>, 20, false, 1));
+    }
+    int zero = 0;
+    CK(cudaMemcpyToSymbol(g_extras, &zero, sizeof(int)));
   }
   if (on("power")) {
     // steady-state cost under load: the 10-MMA pattern on all 148 SMs for ~10 ms per launch, 12 launches back to back,
