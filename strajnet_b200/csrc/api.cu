@@ -254,6 +254,64 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     tc_gemm(c, t);
     c.ws.release(mk);
   };
+  // The flow branch (patch_embed_flow -> flow_layer) and the raster branch (patch embeds -> basic_layers[0]) are two
+  // independent chains of the SAME shape (2 Swin blocks, C = 96, P x P tokens) until `x + flow_x` (modules.py:613): in
+  // bf16 mode they run in lock step, each fused kernel launched ONCE for both branches (half of the CTAs each).  These
+  // kernels are bound by per-tile hand-off latency at 3.5 tiles per SM; twice the tiles per launch is nearly free.
+  static const bool lock_off = getenv("SJ_DISABLE_LOCKSTEP") != nullptr;
+  const SjBasicLayerW& lf = w.flow_layer;
+  const SjBasicLayerW& l0 = w.layers[0];
+  bool lockstep = pe_tc && !lock_off && getenv("SJ_DISABLE_FUSED_WMSA") == nullptr && getenv("SJ_DISABLE_FUSED_MLP") == nullptr &&
+                  lf.depth == 2 && l0.depth == 2 && lf.dim == 96 && l0.dim == 96 && lf.heads == 3 && l0.heads == 3 &&
+                  lf.has_down && l0.has_down && lf.blocks_host && l0.blocks_host && tc_wmsa_supported(B, P, P, 96, 3, 8, 0) &&
+                  tc_wmsa_supported(B, P, P, 96, 3, 8, 4) && tc_gemm_stats_ok(96);
+  if (lockstep)
+    for (int i = 0; i < 2; ++i)
+      lockstep = lockstep && lf.blocks_host[i].qkv_ln.w_tc && l0.blocks_host[i].qkv_ln.w_tc &&
+                 tc_mlp96_supported(96, 384, lf.blocks_host[i]) && tc_mlp96_supported(96, 384, l0.blocks_host[i]);
+  void* x1 = c.alloc_act(B * L0 / 4 * 2 * E);
+  void* x2 = c.alloc_act(B * L0 / 16 * 4 * E);
+  if (lockstep) {
+    const size_t ntok = (size_t)B * L0;
+    void* xm = c.alloc_act(ntok * E);                      // raster-branch tokens (f0 holds the flow branch)
+    float* pm_mean = (float*)c.alloc(ntok * 4);
+    float* pm_rstd = (float*)c.alloc(ntok * 4);
+    {
+      void* cf = c.alloc_act(ntok * E);
+      embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
+      SjNorm none{};
+      pe_combine(c, cf, nullptr, B, P, 0, w.pe_flow.norm, none, w.flow_norm, f0, pe_mean, pe_rstd);
+      void* cv = c.alloc_act(ntok * E);
+      void* cm = c.alloc_act((size_t)B * 4096 * E);
+      embed_tc(ogm, ogm_type, S, 11, 2, w.pe_vec, cv);
+      embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
+      pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, xm, pm_mean, pm_rstd);
+    }
+    void* t1[2] = {c.alloc_act(ntok * E), c.alloc_act(ntok * E)};    // x + attention
+    void* mid[2] = {c.alloc_act(ntok * E), c.alloc_act(ntok * E)};   // output of block 0
+    float* m2[2] = {(float*)c.alloc(ntok * 4), (float*)c.alloc(ntok * 4)};
+    float* r2[2] = {(float*)c.alloc(ntok * 4), (float*)c.alloc(ntok * 4)};
+    float* nm[2] = {(float*)c.alloc(ntok * 4), (float*)c.alloc(ntok * 4)};  // norm1 statistics for block 1
+    float* nr[2] = {(float*)c.alloc(ntok * 4), (float*)c.alloc(ntok * 4)};
+    const void* cur[2] = {f0, xm};
+    const float* cm_[2] = {pe_mean, pm_mean};
+    const float* cr_[2] = {pe_rstd, pm_rstd};
+    for (int i = 0; i < 2; ++i) {
+      const SjSwinBlockW* wb[2] = {&lf.blocks_host[i], &l0.blocks_host[i]};
+      void* dst[2] = {i == 0 ? mid[0] : full[0], i == 0 ? mid[1] : full[1]};
+      tc_wmsa_pair(c, cur, t1, cm_, cr_, wb, B, P, P, i == 0 ? 0 : 4, m2, r2);
+      const void* t1c[2] = {t1[0], t1[1]};
+      const float* m2c[2] = {m2[0], m2[1]};
+      const float* r2c[2] = {r2[0], r2[1]};
+      float* none2[2] = {nullptr, nullptr};
+      tc_mlp96_pair(c, t1c, dst, m2c, r2c, wb, (int)ntok, i == 0 ? nm : none2, i == 0 ? nr : none2);
+      cur[0] = dst[0]; cur[1] = dst[1];
+      cm_[0] = nm[0]; cm_[1] = nm[1];
+      cr_[0] = nr[0]; cr_[1] = nr[1];
+    }
+    patch_merging_impl(c, full[0], flow_x, lf.down, nullptr, B, P, P, 96);
+    patch_merging_impl(c, full[1], x1, l0.down, flow_x, B, P, P, 96);  // + flow_x (modules.py:613)
+  } else {
   if (pe_tc) {
     void* cf = c.alloc_act(B * L0 * E);
     embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
@@ -286,10 +344,9 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     p.gf = w.all_patch_norm.g; p.bf = w.all_patch_norm.b; p.y = x0; p.B = B; p.E = E;
     patch_embed(c, p);
   }
-  void* x1 = c.alloc_act(B * L0 / 4 * 2 * E);
-  void* x2 = c.alloc_act(B * L0 / 16 * 4 * E);
   basic_layer_impl(c, x0, x1, full[1], w.layers[0], flow_x, B, P, P, 8, pe_stats ? pe_mean : nullptr,
                    pe_stats ? pe_rstd : nullptr);  // + flow_x (modules.py:613)
+  }
   basic_layer_impl(c, x1, x2, full[2], w.layers[1], nullptr, B, P / 2, P / 2, 8);
   basic_layer_impl(c, x2, nullptr, full[3], w.layers[2], nullptr, B, P / 4, P / 4, 8);
   if (large) {  // centre crops (modules.py:614-622)

@@ -212,11 +212,18 @@ bool tc_wmsa_supported(int B, int H, int W, int C, int heads, int ws, int shift)
 void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
              int H, int W, int shift, float* mean2, float* rstd2);
 
+// two independent problems of the same geometry in one launch (the encoder's flow and raster branches in lock step)
+void tc_wmsa_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],
+                  const SjSwinBlockW* const w[2], int B, int H, int W, int shift, float* const mean2[2],
+                  float* const rstd2[2]);
+
 // Fused MLP half of a C = 96 Swin block (tc_mlp.cu): out = x + fc2(GELU(fc1(LN(x)))), bf16 [M, 96]; mean/rstd = norm2
 // statistics of x; st_mean/st_rstd (optional) receive the eps-1e-5 LayerNorm statistics of the output rows
 bool tc_mlp96_supported(int C, int hidden, const SjSwinBlockW& w);
 void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int M,
               float* st_mean, float* st_rstd);
+void tc_mlp96_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],
+                   const SjSwinBlockW* const w[2], int M, float* const st_mean[2], float* const st_rstd[2]);
 
 // tcgen05 decoder head (tc_outconv.cu): bf16 inputs [B*8,256,256,48], fp32 logits out
 void tc_out_conv(Ctx& c, const void* x_occ, const void* x_flow, const void* w_tc, const float* bias, int B,

@@ -48,6 +48,7 @@ enum { B_XFULL = 0, B_XEMPTY, B_WFULL, B_Q0, B_Q1, B_Q2, B_Q3, B_HFULL0, B_HFULL
 
 struct MlpP {
   int M, num_tiles;
+  int ctas;            // CTAs serving this group (a launch may carry two independent groups: different x / weights)
   const bf16* x;       // [M, 96] input of the MLP half (= residual)
   bf16* out;           // [M, 96]
   const float* mean;   // norm2 statistics of x
@@ -59,11 +60,22 @@ struct MlpP {
   float* st_rstd;
 };
 
+struct MlpPPair { MlpP g[2]; };
+struct PairMaps { CUtensorMap m[2][3]; };
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
-                const __grid_constant__ CUtensorMap mapW2, const MlpP p) {
+tc_mlp96_kernel(const __grid_constant__ PairMaps maps, const MlpPPair pp) {
+  // group of this CTA: CTAs [0, pp.g[0].ctas) run group 0, the rest group 1 (same shapes, other tensors: the flow / raster
+  // branches of the encoder in lock step).  Both parameter sets sit in one array so that the choice is a constant-bank
+  // offset, not a select per field.
+  const int grp = blockIdx.x >= (unsigned)pp.g[0].ctas ? 1 : 0;
+  const MlpP& p = pp.g[grp];
+  const CUtensorMap* mapX = &maps.m[grp][0];
+  const CUtensorMap* mapW1 = &maps.m[grp][1];
+  const CUtensorMap* mapW2 = &maps.m[grp][2];
+  const int cta = (int)blockIdx.x - (grp ? pp.g[0].ctas : 0), nctas = p.ctas;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -73,9 +85,9 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapX);
-    prefetch_tmap(&mapW1);
-    prefetch_tmap(&mapW2);
+    prefetch_tmap(mapX);
+    prefetch_tmap(mapW1);
+    prefetch_tmap(mapW2);
     const int counts[B_COUNT] = {1, 1, 1, 1, 1, 1, 1, 8, 8, 1, 1, 1, 8};
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
     fence_barrier_init();
@@ -100,14 +112,14 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       mbar_expect_tx(&bar[B_WFULL], 3 * W1_CHUNK + 12 * W2_CHUNK);
       for (int c = 0; c < 3; ++c)
         for (int hf = 0; hf < 2; ++hf)
-          tma_load_2d(smem + OFF_W1 + c * W1_CHUNK + hf * 192 * 64, &mapW1, &bar[B_WFULL], c * 32, hf * 192);
-      for (int c = 0; c < 12; ++c) tma_load_2d(smem + OFF_W2 + c * W2_CHUNK, &mapW2, &bar[B_WFULL], c * 32, 0);
+          tma_load_2d(smem + OFF_W1 + c * W1_CHUNK + hf * 192 * 64, mapW1, &bar[B_WFULL], c * 32, hf * 192);
+      for (int c = 0; c < 12; ++c) tma_load_2d(smem + OFF_W2 + c * W2_CHUNK, mapW2, &bar[B_WFULL], c * 32, 0);
       pdl_wait();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);
         mbar_expect_tx(&bar[B_XFULL], 3 * X_CHUNK);
-        for (int c = 0; c < 3; ++c) tma_load_2d(smem + OFF_X + c * X_CHUNK, &mapX, &bar[B_XFULL], c * 32, tile * 128);
+        for (int c = 0; c < 3; ++c) tma_load_2d(smem + OFF_X + c * X_CHUNK, mapX, &bar[B_XFULL], c * 32, tile * 128);
       }
     }
   } else if (warp == 1) {
@@ -117,7 +129,7 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const uint32_t w2_lo = desc_lo(smem_u32(smem + OFF_W2)), h_lo = desc_lo(smem_u32(smem + OFF_H));
     mbar_wait(&bar[B_WFULL], 0);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
       const uint32_t ph = it & 1;
       mbar_wait(&bar[B_XFULL], ph);
       tc_fence_after();
@@ -164,7 +176,7 @@ tc_mlp96_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const float* b1 = vec + HID;
     const float* b2 = vec + 2 * HID;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
       const uint32_t ph = it & 1;
       const long long row = (long long)tile * 128 + r;
       const bool valid = row < p.M;
@@ -295,37 +307,60 @@ bool tc_mlp96_supported(int Cc, int hidden, const SjSwinBlockW& w) {
   return Cc == C && hidden == HID && w.fc1.w_tc && w.fc1.tc_colsum && w.fc1.tc_bias && w.fc2.w_tc && w.fc2.b;
 }
 
-// out = x + fc2(GELU(fc1(LN(x)))) for x, out bf16 [M, 96]; mean/rstd = norm2 statistics of x
-void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int M,
-              float* st_mean, float* st_rstd) {
+// out = x + fc2(GELU(fc1(LN(x)))) for x, out bf16 [M, 96]; mean/rstd = norm2 statistics of x.  groups = 2: two independent
+// problems of the same size in ONE launch (half of the CTAs each)
+static void tc_mlp96_launch(Ctx& c, int groups, const void* const* x, void* const* out, const float* const* mean,
+                            const float* const* rstd, const SjSwinBlockW* const* w, int M, float* const* st_mean,
+                            float* const* st_rstd) {
   if (!c.ok() || c.dry) return;
-  if (!tc_mlp96_supported(C, HID, w) || !mean || !rstd) { c.fail(SJ_EINVAL); return; }
-  CUtensorMap mapX, mapW1, mapW2;
-  uint64_t dx[2] = {(uint64_t)C, (uint64_t)M};
-  uint64_t sx[1] = {(uint64_t)C * 2};
-  uint32_t bx[2] = {32, 128};
-  uint64_t d1[2] = {(uint64_t)C, (uint64_t)HID};
-  uint32_t b1[2] = {32, 192};
-  uint64_t d2[2] = {(uint64_t)HID, (uint64_t)C};
-  uint64_t s2[1] = {(uint64_t)HID * 2};
-  uint32_t b2[2] = {32, (uint32_t)C};
-  if (!encode_tmap(&mapX, x, 2, dx, sx, bx, 64) || !encode_tmap(&mapW1, w.fc1.w_tc, 2, d1, sx, b1, 64) ||
-      !encode_tmap(&mapW2, w.fc2.w_tc, 2, d2, s2, b2, 64)) {
-    snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_mlp96)");
-    c.fail(SJ_ECUDA);
-    return;
+  PairMaps pm;
+  CUtensorMap (&maps)[2][3] = pm.m;
+  MlpPPair ppair = {};
+  MlpP (&pp)[2] = ppair.g;
+  const int tiles = cdiv(M, 128);
+  int per = tiles < num_sms() / groups ? tiles : num_sms() / groups;
+  for (int g = 0; g < groups; ++g) {
+    if (!tc_mlp96_supported(C, HID, *w[g]) || !mean[g] || !rstd[g]) { c.fail(SJ_EINVAL); return; }
+    uint64_t dx[2] = {(uint64_t)C, (uint64_t)M};
+    uint64_t sx[1] = {(uint64_t)C * 2};
+    uint32_t bx[2] = {32, 128};
+    uint64_t d1[2] = {(uint64_t)C, (uint64_t)HID};
+    uint32_t b1[2] = {32, 192};
+    uint64_t d2[2] = {(uint64_t)HID, (uint64_t)C};
+    uint64_t s2[1] = {(uint64_t)HID * 2};
+    uint32_t b2[2] = {32, (uint32_t)C};
+    if (!encode_tmap(&maps[g][0], x[g], 2, dx, sx, bx, 64) || !encode_tmap(&maps[g][1], w[g]->fc1.w_tc, 2, d1, sx, b1, 64) ||
+        !encode_tmap(&maps[g][2], w[g]->fc2.w_tc, 2, d2, s2, b2, 64)) {
+      snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_mlp96)");
+      c.fail(SJ_ECUDA);
+      return;
+    }
+    MlpP& p = pp[g];
+    p.M = M; p.num_tiles = tiles; p.ctas = per;
+    p.x = (const bf16*)x[g]; p.out = (bf16*)out[g]; p.mean = mean[g]; p.rstd = rstd[g];
+    p.colsum = w[g]->fc1.tc_colsum; p.bias1 = w[g]->fc1.tc_bias; p.bias2 = w[g]->fc2.b;
+    p.st_mean = st_mean ? st_mean[g] : nullptr; p.st_rstd = st_rstd ? st_rstd[g] : nullptr;
   }
-  MlpP p{};
-  p.M = M; p.num_tiles = cdiv(M, 128);
-  p.x = (const bf16*)x; p.out = (bf16*)out; p.mean = mean; p.rstd = rstd;
-  p.colsum = w.fc1.tc_colsum; p.bias1 = w.fc1.tc_bias; p.bias2 = w.fc2.b;
-  p.st_mean = st_mean; p.st_rstd = st_rstd;
+  if (groups == 1) {
+    pp[1] = pp[0];
+    for (int i = 0; i < 3; ++i) maps[1][i] = maps[0][i];
+  }
   if (!SJ_SMEM_LIMIT_OK((tc_mlp96_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  SJ_LAUNCH(c, "tc_mlp96", tc_mlp96_kernel, grid, NTHREADS, 1024 + SMEM_BYTES, mapX, mapW1, mapW2, p);
+  SJ_LAUNCH(c, "tc_mlp96", tc_mlp96_kernel, groups * per, NTHREADS, 1024 + SMEM_BYTES, pm, ppair);
+}
+
+void tc_mlp96(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int M,
+              float* st_mean, float* st_rstd) {
+  const SjSwinBlockW* wp = &w;
+  tc_mlp96_launch(c, 1, &x, &out, &mean, &rstd, &wp, M, &st_mean, &st_rstd);
+}
+
+void tc_mlp96_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],
+                   const SjSwinBlockW* const w[2], int M, float* const st_mean[2], float* const st_rstd[2]) {
+  tc_mlp96_launch(c, 2, x, out, mean, rstd, w, M, st_mean, st_rstd);
 }
 
 }  // namespace sj

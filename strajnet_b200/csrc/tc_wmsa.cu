@@ -61,6 +61,7 @@ enum { B_XFULL = 0, B_XEMPTY, B_WQFULL, B_WQEMPTY, B_WPFULL, B_WPEMPTY, B_QKV, B
 
 struct WmsaP {
   int B, H, W, shift, num_tiles, nW, wpr;  // wpr = windows per row (W/8)
+  int ctas;  // CTAs serving this group (a launch may carry two independent groups: different x / weights)
   const bf16* x;
   bf16* out;
   const float* mean;
@@ -72,6 +73,9 @@ struct WmsaP {
   float* mean2;        // optional: norm2 statistics of the output rows
   float* rstd2;
 };
+
+struct WmsaPPair { WmsaP g[2]; };
+struct PairMaps { CUtensorMap m[2][3]; };
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -95,8 +99,16 @@ __device__ __forceinline__ void store_row64(uint8_t* tile, int r, const float* v
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2)
-tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWq,
-               const __grid_constant__ CUtensorMap mapWp, const WmsaP p) {
+tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
+  // group of this CTA: CTAs [0, pp.g[0].ctas) run group 0, the rest group 1 (same shapes, other tensors: the flow / raster
+  // branches of the encoder in lock step).  Both parameter sets sit in one array so that the choice is a constant-bank
+  // offset, not a select per field.
+  const int grp = blockIdx.x >= (unsigned)pp.g[0].ctas ? 1 : 0;
+  const WmsaP& p = pp.g[grp];
+  const CUtensorMap* mapX = &maps.m[grp][0];
+  const CUtensorMap* mapWq = &maps.m[grp][1];
+  const CUtensorMap* mapWp = &maps.m[grp][2];
+  const int cta = (int)blockIdx.x - (grp ? pp.g[0].ctas : 0), nctas = p.ctas;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -107,9 +119,9 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapX);
-    prefetch_tmap(&mapWq);
-    prefetch_tmap(&mapWp);
+    prefetch_tmap(mapX);
+    prefetch_tmap(mapWq);
+    prefetch_tmap(mapWp);
     const int counts[B_COUNT] = {1, 1, 1, 1, 1, 1, 1, 4, 1, 4, 1, 4, 1, 4};
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
     fence_barrier_init();
@@ -136,7 +148,7 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     if (lane == 0) {
       const int s4 = p.shift >> 2, wq = p.W >> 2, hq = p.H >> 2;
       uint32_t it = 0, hc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);
         mbar_expect_tx(&bar[B_XFULL], 3 * X_CHUNK);
         for (int wt = 0; wt < 2; ++wt) {
@@ -144,7 +156,7 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           for (int quad = 0; quad < 4; ++quad) {
             const int yq = (2 * wi + (quad >> 1) + s4) % hq, xq = (2 * wj + (quad & 1) + s4) % wq;
             for (int c = 0; c < 3; ++c)
-              tma_load_5d(smem + OFF_X + c * X_CHUNK + (wt * 64 + quad * 16) * 64, &mapX, &bar[B_XFULL], c * 32, 0, xq,
+              tma_load_5d(smem + OFF_X + c * X_CHUNK + (wt * 64 + quad * 16) * 64, mapX, &bar[B_XFULL], c * 32, 0, xq,
                           0, b * hq + yq);
           }
         }
@@ -154,10 +166,10 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           mbar_expect_tx(&bar[B_WQFULL], 3 * WQ_CHUNK);
           for (int c = 0; c < 3; ++c)
             for (int part = 0; part < 3; ++part)
-              tma_load_2d(smem + OFF_WQ + c * WQ_CHUNK + part * 32 * 64, &mapWq, &bar[B_WQFULL], c * 32, part * C + h * 32);
+              tma_load_2d(smem + OFF_WQ + c * WQ_CHUNK + part * 32 * 64, mapWq, &bar[B_WQFULL], c * 32, part * C + h * 32);
           mbar_wait(&bar[B_WPEMPTY], (hc & 1) ^ 1);
           mbar_expect_tx(&bar[B_WPFULL], WP_TILE);
-          tma_load_2d(smem + OFF_WP, &mapWp, &bar[B_WPFULL], h * 32, 0);
+          tma_load_2d(smem + OFF_WP, mapWp, &bar[B_WPFULL], h * 32, 0);
         }
       }
     }
@@ -171,7 +183,7 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const uint32_t k_lo = desc_lo(smem_u32(smem + OFF_K)), v_lo = desc_lo(smem_u32(smem + OFF_V));
     const uint32_t p_lo = desc_lo(smem_u32(smem + OFF_P)), ao_lo = desc_lo(smem_u32(smem + OFF_AO));
     uint32_t it = 0, hc = 0;  // tiles / heads processed by this CTA
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
       mbar_wait(&bar[B_XFULL], it & 1);
       for (int h = 0; h < NH; ++h, ++hc) {
         const uint32_t hp = hc & 1;
@@ -229,7 +241,7 @@ tc_wmsa_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const int base_q = (rw + 7) * 15 + cw + 7;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint32_t it = 0, hc = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
       const int gw = 2 * tile + wt, b = gw / p.nW, wl = gw % p.nW, wi = wl / p.wpr, wj = wl % p.wpr;
       const int ys = 8 * wi + rw, xs = 8 * wj + cw;
       const long long tok = ((long long)b * p.H + (ys + p.shift) % p.H) * p.W + (xs + p.shift) % p.W;
@@ -370,43 +382,69 @@ bool tc_wmsa_supported(int B, int H, int W, int Cc, int heads, int ws, int shift
   return ((long long)B * (H / 8) * (W / 8)) % 2 == 0;
 }
 
-// x, out: bf16 [B, H*W, 96]; mean/rstd: fp32 [B*H*W] (norm1 statistics of x); w: norm1-folded qkv (tensor-core copy)
-void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
-             int H, int W, int shift, float* mean2, float* rstd2) {
+// x, out: bf16 [B, H*W, 96]; mean/rstd: fp32 [B*H*W] (norm1 statistics of x); w: norm1-folded qkv (tensor-core copy).
+// groups = 2: two independent problems of the same geometry in ONE launch (half of the CTAs each)
+static void tc_wmsa_launch(Ctx& c, int groups, const void* const* x, void* const* out, const float* const* mean,
+                           const float* const* rstd, const SjSwinBlockW* const* w, int B, int H, int W, int shift,
+                           float* const* mean2, float* const* rstd2) {
   if (!c.ok() || c.dry) return;
-  if (!w.qkv_ln.w_tc || !w.qkv_ln.tc_colsum || !w.qkv_ln.tc_bias || !w.proj.w_tc || !w.proj.b || !w.rpb_table) {
-    c.fail(SJ_EINVAL);
-    return;
+  PairMaps pm;
+  CUtensorMap (&maps)[2][3] = pm.m;
+  WmsaPPair ppair = {};
+  WmsaP (&pp)[2] = ppair.g;
+  const int tiles = B * (H / 8) * (W / 8) / 2;
+  const int cap = 2 * num_sms() / groups;  // two CTAs per SM
+  const int per = tiles < cap ? tiles : cap;
+  for (int g = 0; g < groups; ++g) {
+    const SjSwinBlockW& wg = *w[g];
+    if (!wg.qkv_ln.w_tc || !wg.qkv_ln.tc_colsum || !wg.qkv_ln.tc_bias || !wg.proj.w_tc || !wg.proj.b || !wg.rpb_table) {
+      c.fail(SJ_EINVAL);
+      return;
+    }
+    uint64_t dx[5] = {(uint64_t)C, 4, (uint64_t)W / 4, 4, (uint64_t)B * H / 4};
+    uint64_t sx[4] = {(uint64_t)C * 2, (uint64_t)4 * C * 2, (uint64_t)W * C * 2, (uint64_t)4 * W * C * 2};
+    uint32_t bx[5] = {32, 4, 1, 4, 1};
+    uint64_t dq[2] = {(uint64_t)C, (uint64_t)3 * C};
+    uint64_t sq[1] = {(uint64_t)C * 2};
+    uint32_t bq[2] = {32, 32};
+    uint64_t dp[2] = {(uint64_t)C, (uint64_t)C};
+    uint32_t bp[2] = {32, 96};
+    if (!encode_tmap(&maps[g][0], x[g], 5, dx, sx, bx, 64) || !encode_tmap(&maps[g][1], wg.qkv_ln.w_tc, 2, dq, sq, bq, 64) ||
+        !encode_tmap(&maps[g][2], wg.proj.w_tc, 2, dp, sq, bp, 64)) {
+      snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_wmsa)");
+      c.fail(SJ_ECUDA);
+      return;
+    }
+    WmsaP& p = pp[g];
+    p.B = B; p.H = H; p.W = W; p.shift = shift;
+    p.wpr = W / 8; p.nW = (H / 8) * (W / 8);
+    p.num_tiles = tiles; p.ctas = per;
+    p.x = (const bf16*)x[g]; p.out = (bf16*)out[g]; p.mean = mean[g]; p.rstd = rstd[g];
+    p.mean2 = mean2 ? mean2[g] : nullptr; p.rstd2 = rstd2 ? rstd2[g] : nullptr;
+    p.colsum = wg.qkv_ln.tc_colsum; p.biasf = wg.qkv_ln.tc_bias; p.table = wg.rpb_table; p.bproj = wg.proj.b;
   }
-  CUtensorMap mapX, mapWq, mapWp;
-  uint64_t dx[5] = {(uint64_t)C, 4, (uint64_t)W / 4, 4, (uint64_t)B * H / 4};
-  uint64_t sx[4] = {(uint64_t)C * 2, (uint64_t)4 * C * 2, (uint64_t)W * C * 2, (uint64_t)4 * W * C * 2};
-  uint32_t bx[5] = {32, 4, 1, 4, 1};
-  uint64_t dq[2] = {(uint64_t)C, (uint64_t)3 * C};
-  uint64_t sq[1] = {(uint64_t)C * 2};
-  uint32_t bq[2] = {32, 32};
-  uint64_t dp[2] = {(uint64_t)C, (uint64_t)C};
-  uint32_t bp[2] = {32, 96};
-  if (!encode_tmap(&mapX, x, 5, dx, sx, bx, 64) || !encode_tmap(&mapWq, w.qkv_ln.w_tc, 2, dq, sq, bq, 64) ||
-      !encode_tmap(&mapWp, w.proj.w_tc, 2, dp, sq, bp, 64)) {
-    snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_wmsa)");
-    c.fail(SJ_ECUDA);
-    return;
+  if (groups == 1) {
+    pp[1] = pp[0];
+    for (int i = 0; i < 3; ++i) maps[1][i] = maps[0][i];
   }
-  WmsaP p{};
-  p.B = B; p.H = H; p.W = W; p.shift = shift;
-  p.wpr = W / 8; p.nW = (H / 8) * (W / 8);
-  p.num_tiles = B * p.nW / 2;
-  p.x = (const bf16*)x; p.out = (bf16*)out; p.mean = mean; p.rstd = rstd;
-  p.mean2 = mean2; p.rstd2 = rstd2;
-  p.colsum = w.qkv_ln.tc_colsum; p.biasf = w.qkv_ln.tc_bias; p.table = w.rpb_table; p.bproj = w.proj.b;
   const size_t smem = 1024 + SMEM_BYTES;
   if (!SJ_SMEM_LIMIT_OK((tc_wmsa_kernel), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }
-  const int grid = p.num_tiles < 2 * num_sms() ? p.num_tiles : 2 * num_sms();  // two CTAs per SM
-  SJ_LAUNCH(c, "tc_wmsa", tc_wmsa_kernel, grid, NTHREADS, smem, mapX, mapWq, mapWp, p);
+  SJ_LAUNCH(c, "tc_wmsa", tc_wmsa_kernel, groups * per, NTHREADS, smem, pm, ppair);
+}
+
+void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
+             int H, int W, int shift, float* mean2, float* rstd2) {
+  const SjSwinBlockW* wp = &w;
+  tc_wmsa_launch(c, 1, &x, &out, &mean, &rstd, &wp, B, H, W, shift, &mean2, &rstd2);
+}
+
+void tc_wmsa_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],
+                  const SjSwinBlockW* const w[2], int B, int H, int W, int shift, float* const mean2[2],
+                  float* const rstd2[2]) {
+  tc_wmsa_launch(c, 2, x, out, mean, rstd, w, B, H, W, shift, mean2, rstd2);
 }
 
 }  // namespace sj
