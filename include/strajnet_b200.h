@@ -25,7 +25,7 @@
  *   - sj_probe_start / sj_probe_stop: per-thread timing probe for bench.py;
  *   - environment switches read once at first use, kept so that an earlier kernel generation can be re-measured against
  *     its replacement (each selects between two implementations of the same op): SJ_DISABLE_FUSED_WMSA,
- *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION,
+ *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION, SJ_DISABLE_RESADD2, SJ_DISABLE_LOCKSTEP,
  *     SJ_DISABLE_ATTN_MMA, SJ_DISABLE_IM2COL_STAGED, SJ_DISABLE_NORM_FAST, SJ_DISABLE_FG_OFFSET_MMA (fall back to the
  *     previous kernel), SJ_SIDE_STREAM (actor branch on a helper stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue
  *     variants), SJ_NO_PDL (forces the PDL mask to 0).
@@ -274,6 +274,12 @@ int sj_upconv_fwd(const void* x, void* y, const SjLinear* w, int NB, int H, int 
  * skip [B,HW,Cin], src/dst [B,8,HW,Cout] (dst may alias src). */
 int sj_res_add_fwd(const void* skip, const void* src, void* dst, const SjLinear* w, int B, int HW, int Cin, int Cout,
                    int dtype, sj_stream_t stream);
+/* Both skip connections that meet at 64x64, modules.py:750-757 (res_layer[1] on res0) and :762-765 (res_f on flow_res, added
+ * to x AFTER the res0 add): dst_a = src + ELU(skip_a . Wa_eff[t] + ba), dst_b = dst_a + ELU(skip_b . Wb_eff[t] + bb);
+ * skips [B,HW,Cin], src / dst [B,8,HW,Cout]; dst_a may alias src.  One fused kernel for dtype == SJ_BF16, Cin = 96,
+ * Cout = 128; two sj_res_add_fwd steps otherwise. */
+int sj_res_add2_fwd(const void* skip_a, const void* skip_b, const void* src, void* dst_a, void* dst_b, const SjLinear* wa,
+                    const SjLinear* wb, int B, int HW, int Cin, int Cout, int dtype, sj_stream_t stream);
 /* The two heads, modules.py:767-770 (`output_layer` on x, `output_layer_f` on the flow branch, Conv2D 3x3 SAME 48->2,
  * concatenated) + the transpose of :838: x_occ, x_flow [B*8,256,256,48] -> out; out_layout 0/1 as sj_decoder_fwd,
  * 2 = quantised submission bytes uint8 [B,256,256,32] (inference.py:124-136,160-182). */
@@ -320,7 +326,13 @@ int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, c
  * compute_occupancy_flow_metrics' no_warp. */
 enum {
   SJ_EVAL_USE_FOCAL = 1, SJ_EVAL_NO_USE_WARP = 2, SJ_EVAL_USE_PRED = 4, SJ_EVAL_USE_GT = 8,
-  SJ_EVAL_PRED_IS_PROB = 16, SJ_EVAL_LOSS = 32, SJ_EVAL_METRICS = 64, SJ_EVAL_METRICS_NO_WARP = 128
+  SJ_EVAL_PRED_IS_PROB = 16, SJ_EVAL_LOSS = 32, SJ_EVAL_METRICS = 64, SJ_EVAL_METRICS_NO_WARP = 128,
+  /* tf.keras.metrics.AUC label semantics.  Default (flag clear): y_true is cast to bool -- tf.keras <= 2.5 and >= 2.8.
+   * Flag set: tf.keras 2.6 / 2.7, whose evenly-spaced-threshold path (_update_confusion_matrix_variables_optimized) keeps
+   * the label as a float: a sample adds y_true to the true-positive mass and 1 - y_true to the false-positive mass.
+   * Only vehicles_flow_warped_occupancy_auc can differ (its label is the fractional flow-grounded prediction,
+   * occu_metric.py:121-123); the reference pins no TensorFlow version, so the caller chooses. */
+  SJ_EVAL_AUC_FLOAT_LABELS = 256
 };
 #define SJ_EVAL_OUT_FLOATS 19
 typedef struct { int flags; float ogm_weight; float occ_weight; float flow_origin_weight; float replica; } SjEvalParams;

@@ -62,15 +62,28 @@ def auc_thresholds() -> np.ndarray:
     return np.asarray([0.0 - EPS] + t + [1.0 + EPS], dtype=np.float32)
 
 
-def keras_pr_auc(y_true: Tensor, y_pred: Tensor) -> Tensor:
-    """occu_metric.py:152-175 (`_compute_occupancy_auc`): one update_state, then result()."""
-    lab = y_true.reshape(-1) != 0
+def keras_pr_auc(y_true: Tensor, y_pred: Tensor, float_labels: bool = False) -> Tensor:
+    """occu_metric.py:152-175 (`_compute_occupancy_auc`): one update_state, then result().
+
+    `float_labels` selects which tf.keras the numbers are meant to reproduce (the reference pins no version):
+    False: y_true is cast to bool (tf.keras <= 2.5, and >= 2.8 where the cast was restored);
+    True:  tf.keras 2.6 / 2.7 evenly-spaced-threshold path (`_update_confusion_matrix_variables_optimized`), which keeps the
+           label as a float: true-positive mass += y_true, false-positive mass += 1 - y_true, false negatives = total
+           label mass - true positives.  Identical for 0/1 labels; differs for the fractional label of
+           vehicles_flow_warped_occupancy_auc (arguments swapped at occu_metric.py:121-123)."""
     pred = y_pred.reshape(-1).float()
     thr = torch.from_numpy(auc_thresholds())
-    above = pred.unsqueeze(0) > thr.unsqueeze(1)  # [T, n]
-    tp = (above & lab).sum(1).float()
-    fp = (above & ~lab).sum(1).float()
-    fn = ((~above) & lab).sum(1).float()
+    above = (pred.unsqueeze(0) > thr.unsqueeze(1)).float()  # [T, n]
+    if float_labels:
+        lab = y_true.reshape(-1).float()
+        tp = (above * lab).sum(1)
+        fp = (above * (1.0 - lab)).sum(1)
+        fn = lab.sum() - tp
+    else:
+        lab = (y_true.reshape(-1) != 0).float()
+        tp = (above * lab).sum(1)
+        fp = (above * (1.0 - lab)).sum(1)
+        fn = ((1.0 - above) * lab).sum(1)
     return interpolate_pr_auc(tp, fp, fn)
 
 
@@ -163,7 +176,7 @@ def ogm_flow_loss(pred: Tensor, gt_obs: Tensor, gt_occ: Tensor, gt_flow: Tensor,
 
 
 def occupancy_flow_metrics(pred: Tensor, gt_obs: Tensor, gt_occ: Tensor, gt_flow: Tensor, origin: Tensor,
-                           pred_is_logits: bool = True, no_warp: bool = False) -> Dict[str, Tensor]:
+                           pred_is_logits: bool = True, no_warp: bool = False, auc_float_labels: bool = False) -> Dict[str, Tensor]:
     """compute_occupancy_flow_metrics (occu_metric.py:26-140); `pred_is_logits` applies
     `_apply_sigmoid_to_occupancy_logits` (train.py:142-154) first."""
     B, H, W, _ = pred.shape
@@ -181,9 +194,9 @@ def occupancy_flow_metrics(pred: Tensor, gt_obs: Tensor, gt_occ: Tensor, gt_flow
         lo, lc, pf = _split(pred, k)
         po, pc = (torch.sigmoid(lo), torch.sigmoid(lc)) if pred_is_logits else (lo, lc)
         to, tc, tf_, org = gt_obs[:, k], gt_occ[:, k], gt_flow[:, k], origin[:, k].unsqueeze(-1)
-        acc["vehicles_observed_auc"].append(keras_pr_auc(to, po))
+        acc["vehicles_observed_auc"].append(keras_pr_auc(to, po, auc_float_labels))
         acc["vehicles_observed_iou"].append(soft_iou(to, po))
-        acc["vehicles_occluded_auc"].append(keras_pr_auc(tc, pc))
+        acc["vehicles_occluded_auc"].append(keras_pr_auc(tc, pc, auc_float_labels))
         acc["vehicles_occluded_iou"].append(soft_iou(tc, pc))
         # _compute_flow_epe (occu_metric.py:204-250)
         exists = ((tf_[..., 0] != 0) | (tf_[..., 1] != 0)).float()
@@ -195,7 +208,7 @@ def occupancy_flow_metrics(pred: Tensor, gt_obs: Tensor, gt_occ: Tensor, gt_flow
             pred_all = torch.clamp(po + pc, 0, 1)
             wp = bilinear_sample_zero(org, ident + pf)[..., 0]
             g = pred_all * wp
-            acc["vehicles_flow_warped_occupancy_auc"].append(keras_pr_auc(g, true_all))  # swapped, as in the reference
+            acc["vehicles_flow_warped_occupancy_auc"].append(keras_pr_auc(g, true_all, auc_float_labels))  # swapped, as in the reference
             acc["vehicles_flow_warped_occupancy_iou"].append(soft_iou(g, true_all))
     return {n: (torch.stack(v).sum() / len(v) if v else torch.tensor(0.0)) for n, v in acc.items()}
 

@@ -562,6 +562,20 @@ void res_add(Ctx& c, const void* skip, const SjLinear& w, const void* src, void*
 // Last stage of both branches + the two heads (modules.py:746-749 with i = 3, :732-737 second iteration, :767-770, :838):
 // x3, f3 [B*8,128,128,96] -> out.  bf16: the 96 -> 48 up-convolutions are fused with the heads' channel contraction
 // (tc_upconv4h: x4 / f4 never reach HBM), head_tapsum finishes the 3x3 sums; otherwise up-convolution, then out_conv.
+// dst_a = src + ELU(skip_a . Wa_eff[t] + ba); dst_b = dst_a + ELU(skip_b . Wb_eff[t] + bb): the res0 skip of the raster
+// branch and the flow_res skip of the flow branch, which uses x AFTER the res0 add (modules.py:750-757, :762-765)
+void res_add2(Ctx& c, const void* skip_a, const void* skip_b, const SjLinear& wa, const SjLinear& wb, const void* src,
+              void* dst_a, void* dst_b, int B, int HW, int Cin, int Cout) {
+  static const bool off = getenv("SJ_DISABLE_RESADD2") != nullptr;
+  if (c.dtype == SJ_BF16 && !off && wa.w_tc && wb.w_tc && wa.b && wb.b && tc_resadd2_supported(HW, Cin, Cout)) {
+    RoleScope r(c, "dec.res1");
+    tc_resadd2(c, skip_a, skip_b, src, dst_a, dst_b, wa.w_tc, wa.b, wb.w_tc, wb.b, B, HW);
+    return;
+  }
+  { RoleScope r(c, "dec.res1"); res_add(c, skip_a, wa, src, dst_a, B, HW, Cin, Cout); }
+  { RoleScope r(c, "dec.resf"); res_add(c, skip_b, wb, dst_a, dst_b, B, HW, Cin, Cout); }
+}
+
 void decoder_tail_impl(Ctx& c, const void* x3, const void* f3, void* out, const SjDecoderW& w, int B, int out_layout) {
   const int NB = B * 8;
   size_t mark = c.ws.mark();
@@ -598,9 +612,7 @@ void decoder_impl(Ctx& c, const void* x, const void* flow_res, const void* res0,
   { RoleScope r(c, "dec.upconv0"); upconv(c, x, x1, w.upconv[0], NB, 16, 384, 192); }
   { RoleScope r(c, "dec.res0"); res_add(c, res1, w.res[0], x1, x1, B, 32 * 32, 192, 192); }
   { RoleScope r(c, "dec.upconv1"); upconv(c, x1, x2, w.upconv[1], NB, 32, 192, 128); }
-  { RoleScope r(c, "dec.res1"); res_add(c, res0, w.res[1], x2, x2, B, 64 * 64, 96, 128); }
-  // uses x AFTER the res0 add (modules.py:762-765)
-  { RoleScope r(c, "dec.resf"); res_add(c, flow_res, w.res_f, x2, fx, B, 64 * 64, 96, 128); }
+  res_add2(c, res0, flow_res, w.res[1], w.res_f, x2, x2, fx, B, 64 * 64, 96, 128);
   { RoleScope r(c, "dec.upconv2"); upconv(c, x2, x3, w.upconv[2], NB, 64, 128, 96); }
   { RoleScope r(c, "dec.upconvf0"); upconv(c, fx, f3, w.upconv_f[0], NB, 64, 128, 96); }
   decoder_tail_impl(c, x3, f3, out, w, B, out_layout);
@@ -1039,6 +1051,13 @@ int sj_out_head_fwd(const void* x_occ, const void* x_flow, void* out, const SjDe
   });
 }
 
+int sj_res_add2_fwd(const void* skip_a, const void* skip_b, const void* src, void* dst_a, void* dst_b, const SjLinear* wa,
+                    const SjLinear* wb, int B, int HW, int Cin, int Cout, int dtype, sj_stream_t stream) {
+  SJ_REQUIRE(skip_a && skip_b && src && dst_a && dst_b && wa && wb && wa->w && wa->b && wb->w && wb->b && B > 0 && HW > 0 &&
+             Cin % 8 == 0 && Cout % 8 == 0);
+  return run(nullptr, 0, dtype, stream,
+             [&](Ctx& c) { res_add2(c, skip_a, skip_b, *wa, *wb, src, dst_a, dst_b, B, HW, Cin, Cout); });
+}
 size_t sj_decoder_tail_workspace_bytes(int B, int dtype) {
   SjDecoderW z{};
   return measure(dtype, [&](Ctx& c) { decoder_tail_impl(c, nullptr, nullptr, nullptr, z, B, 1); });

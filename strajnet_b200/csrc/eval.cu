@@ -26,6 +26,7 @@ struct EvalP {
   int B, H, W, flags, nblk;
   double* partial;  // [8][nblk][NACC]
   int* hist;        // [8][NAUC][2][NBIN]
+  float* fhist;     // [8][NAUC][2][NBIN] label MASS per bin (SJ_EVAL_AUC_FLOAT_LABELS), else unused
 };
 
 __device__ __forceinline__ float sce(float z, float x) {  // tf.nn.sigmoid_cross_entropy_with_logits
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
   pdl_wait();
   pdl_trigger();
   __shared__ int hist_s[HIST];
+  float* fh_s = reinterpret_cast<float*>(hist_s);  // same storage: one of the two kinds of histogram is in use
   __shared__ float thr_s[100];
   __shared__ float red_s[NT / 32][NACC];
   const int tid = threadIdx.x, lane = tid % 32, k = blockIdx.y;
@@ -88,7 +90,8 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
   const bool use_focal = p.flags & SJ_EVAL_USE_FOCAL, no_use_warp = p.flags & SJ_EVAL_NO_USE_WARP,
              use_pred = p.flags & SJ_EVAL_USE_PRED, use_gt = p.flags & SJ_EVAL_USE_GT,
              is_prob = p.flags & SJ_EVAL_PRED_IS_PROB, do_loss = p.flags & SJ_EVAL_LOSS,
-             do_metrics = p.flags & SJ_EVAL_METRICS, no_warp_m = p.flags & SJ_EVAL_METRICS_NO_WARP;
+             do_metrics = p.flags & SJ_EVAL_METRICS, no_warp_m = p.flags & SJ_EVAL_METRICS_NO_WARP,
+             float_labels = p.flags & SJ_EVAL_AUC_FLOAT_LABELS;
   const int HW = p.H * p.W;
   float acc[NACC];
 #pragma unroll
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
     const int row = item / xchunks, b = row / p.H, y = row % p.H, x = (item % xchunks) * NT + tid;
     const bool valid = x < p.W;
     int key[NAUC] = {-1, -1, -1, -1};
+    float lab[NAUC] = {0.f, 0.f, 0.f, 0.f};  // label value of each AUC sample (float-label semantics only)
     if (valid) {
       const int pix = y * p.W + x;
       const long long idx = (long long)b * HW + pix;
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
         if (use_gt) {
           const float wo = sample_zero(org, p.H, p.W, (float)x + tf.x, (float)y + tf.y);
           key[3] = (ta != 0.f ? NBIN : 0) + auc_bin(wo * ta, thr_s);
+          lab[3] = ta;
         }
         if (!no_use_warp) {
           const float a = use_pred ? po + pc : sigmoidf(to) + sigmoidf(tc);
@@ -139,18 +144,33 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
       if (do_metrics) {
         key[0] = (to != 0.f ? NBIN : 0) + auc_bin(po, thr_s);
         key[1] = (tc != 0.f ? NBIN : 0) + auc_bin(pc, thr_s);
+        lab[0] = to;
+        lab[1] = tc;
         acc[A_IOU_OBS] += po * to; acc[A_SUM_TO] += to; acc[A_SUM_PO] += po;
         acc[A_IOU_OCC] += pc * tc; acc[A_SUM_TC] += tc; acc[A_SUM_PC] += pc;
         acc[A_EPE] += sqrtf(dx * dx + dy * dy);
         if (!no_warp_m) {
           const float gq = fminf(fmaxf(po + pc, 0.f), 1.f) * wp;
           key[2] = (gq != 0.f ? NBIN : 0) + auc_bin(ta, thr_s);  // swapped arguments, occu_metric.py:121-123
+          lab[2] = gq;  // the fractional flow-grounded prediction is the LABEL here
           acc[A_IOU_G] += ta * gq; acc[A_SUM_G] += gq; acc[A_SUM_TA] += ta;
         }
       }
     }
+    if (float_labels) {
+      // tf.keras >= 2.6 evenly-spaced-threshold path (_update_confusion_matrix_variables_optimized): the label is not cast
+      // to bool; a sample adds y_true to the true-positive mass of its bin and 1 - y_true to the false-positive mass
 #pragma unroll
-    for (int a = 0; a < NAUC; ++a) hist_add(hist_s + a * 2 * NBIN, key[a], lane);
+      for (int a = 0; a < NAUC; ++a)
+        if (key[a] >= 0) {
+          const int bin = key[a] >= NBIN ? key[a] - NBIN : key[a];
+          if (lab[a] != 0.f) atomicAdd(&fh_s[a * 2 * NBIN + NBIN + bin], lab[a]);
+          if (lab[a] != 1.f) atomicAdd(&fh_s[a * 2 * NBIN + bin], 1.0f - lab[a]);
+        }
+    } else {
+#pragma unroll
+      for (int a = 0; a < NAUC; ++a) hist_add(hist_s + a * 2 * NBIN, key[a], lane);
+    }
   }
 #pragma unroll
   for (int i = 0; i < NACC; ++i) {
@@ -163,13 +183,19 @@ __global__ void __launch_bounds__(NT) eval_pass_kernel(const EvalP p) {
     for (int w = 0; w < NT / 32; ++w) s += (double)red_s[w][tid];
     p.partial[((long long)k * p.nblk + blockIdx.x) * NACC + tid] = s;
   }
-  for (int i = tid; i < HIST; i += NT)
-    if (hist_s[i]) atomicAdd(&p.hist[k * HIST + i], hist_s[i]);
+  if (float_labels) {
+    for (int i = tid; i < HIST; i += NT)
+      if (fh_s[i] != 0.f) atomicAdd(&p.fhist[k * HIST + i], fh_s[i]);
+  } else {
+    for (int i = tid; i < HIST; i += NT)
+      if (hist_s[i]) atomicAdd(&p.hist[k * HIST + i], hist_s[i]);
+  }
 }
 
 struct FinP {
   const double* partial;
   const int* hist;
+  const float* fhist;
   int B, H, W, flags, nblk;
   float ogm_weight, occ_weight, flow_origin_weight, replica;
   float* out;  // [SJ_EVAL_OUT_FLOATS]
@@ -201,6 +227,29 @@ __device__ float pr_auc(const int* h) {
   return auc;
 }
 
+// the same integral from label-mass histograms (float-label semantics): tp / fp are sums of masses
+__device__ float pr_auc_f(const float* h) {
+  const float* hf = h;
+  const float* ht = h + NBIN;
+  float total_t = 0.f;
+  for (int j = 0; j < NBIN; ++j) total_t += ht[j];
+  float tp_i = 0.f, fp_i = 0.f;
+  for (int j = 1; j < NBIN; ++j) { tp_i += ht[j]; fp_i += hf[j]; }
+  float auc = 0.f;
+  float tp0 = tp_i, p0 = tp_i + fp_i;
+  for (int i = 1; i < 100; ++i) {
+    tp_i -= ht[i]; fp_i -= hf[i];
+    const float tp1 = tp_i, p1 = tp_i + fp_i, fn1 = total_t - tp_i;
+    const float dtp = tp0 - tp1, dp = p0 - p1;
+    const float slope = div_no_nan(dtp, fmaxf(dp, 0.f));
+    const float intercept = tp1 - slope * p1;
+    const float ratio = (p0 > 0.f && p1 > 0.f) ? div_no_nan(p0, fmaxf(p1, 0.f)) : 1.0f;
+    auc += div_no_nan(slope * (dtp + intercept * logf(ratio)), fmaxf(tp1 + fn1, 0.f));
+    tp0 = tp1; p0 = p1;
+  }
+  return auc;
+}
+
 __global__ void __launch_bounds__(256) eval_finalize_kernel(const FinP p) {
   pdl_wait();
   pdl_trigger();
@@ -215,7 +264,8 @@ __global__ void __launch_bounds__(256) eval_finalize_kernel(const FinP p) {
   }
   if (tid >= 192 && tid < 192 + 8 * NAUC) {
     const int t = tid - 192, k = t / NAUC, a = t % NAUC;
-    aucs[k][a] = pr_auc(p.hist + (k * NAUC + a) * 2 * NBIN);
+    aucs[k][a] = (p.flags & SJ_EVAL_AUC_FLOAT_LABELS) ? pr_auc_f(p.fhist + (k * NAUC + a) * 2 * NBIN)
+                                                       : pr_auc(p.hist + (k * NAUC + a) * 2 * NBIN);
   }
   __syncthreads();
   if (tid != 0) return;
@@ -264,7 +314,7 @@ int eval_blocks() { return 4 * num_sms() / 8 > 0 ? 4 * num_sms() / 8 : 1; }  // 
 }  // namespace
 
 size_t eval_workspace_bytes() {
-  return (size_t)8 * eval_blocks() * NACC * sizeof(double) + (size_t)8 * HIST * sizeof(int) + 512;
+  return (size_t)8 * eval_blocks() * NACC * sizeof(double) + (size_t)2 * 8 * HIST * sizeof(int) + 1024;
 }
 
 void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,
@@ -272,13 +322,14 @@ void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* g
                   float flow_origin_weight, float replica, float* out) {
   const int nblk = eval_blocks();
   double* partial = (double*)c.alloc((size_t)8 * nblk * NACC * sizeof(double));
-  int* hist = (int*)c.alloc((size_t)8 * HIST * sizeof(int));
+  int* hist = (int*)c.alloc((size_t)2 * 8 * HIST * sizeof(int));  // integer counts, then float label masses
   if (!c.ok() || c.dry) return;
   if (!partial || !hist) return;  // workspace overflow is reported by run()
-  if (cudaMemsetAsync(hist, 0, (size_t)8 * HIST * sizeof(int), c.stream) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
-  EvalP p{pred, gt_obs, gt_occ, gt_flow, origin, B, H, W, flags, nblk, partial, hist};
+  if (cudaMemsetAsync(hist, 0, (size_t)2 * 8 * HIST * sizeof(int), c.stream) != cudaSuccess) { c.fail(SJ_ECUDA); return; }
+  float* fhist = reinterpret_cast<float*>(hist + 8 * HIST);
+  EvalP p{pred, gt_obs, gt_occ, gt_flow, origin, B, H, W, flags, nblk, partial, hist, fhist};
   SJ_LAUNCH(c, "eval_pass", eval_pass_kernel, dim3(nblk, 8), NT, 0, p);
-  FinP f{partial, hist, B, H, W, flags, nblk, ogm_weight, occ_weight, flow_origin_weight, replica, out};
+  FinP f{partial, hist, fhist, B, H, W, flags, nblk, ogm_weight, occ_weight, flow_origin_weight, replica, out};
   SJ_LAUNCH(c, "eval_finalize", eval_finalize_kernel, 1, 256, 0, f);
 }
 

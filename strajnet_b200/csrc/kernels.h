@@ -237,6 +237,12 @@ void tc_upconv4h(Ctx& c, const void* x, void* z, const void* w_tc, const float* 
 // 9-tap shifted sum of both heads' projected columns + bias + final layout (headsum.cu); out_layout as out_conv
 void head_tapsum(Ctx& c, const void* z_occ, const void* z_flow, const float* bias, int B, int out_layout, void* out);
 
+// both 64x64 skip connections of the decoder in one kernel (tc_resadd2.cu): dst_a = src + ELU(skip_a . Wa[t] + ba) (may
+// alias src), dst_b = dst_a + ELU(skip_b . Wb[t] + bb); skips bf16 [B,HW,96], src / dst bf16 [B,8,HW,128]
+bool tc_resadd2_supported(int HW, int Cin, int Cout);
+void tc_resadd2(Ctx& c, const void* skip_a, const void* skip_b, const void* src, void* dst_a, void* dst_b, const void* wa_tc,
+                const float* bias_a, const void* wb_tc, const float* bias_b, int B, int HW);
+
 // ---- validation-side loss / metrics (eval.cu) ----------------------------------------------------
 size_t eval_workspace_bytes();
 void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,

@@ -25,7 +25,8 @@ Tensor = torch.Tensor
 LOSS_NAMES = ("observed_xe", "occluded_xe", "flow", "flow_warp_xe")
 METRIC_NAMES = ("vehicles_observed_auc", "vehicles_occluded_auc", "vehicles_observed_iou", "vehicles_occluded_iou",
                 "vehicles_flow_epe", "vehicles_flow_warped_occupancy_auc", "vehicles_flow_warped_occupancy_iou")
-FLAG = dict(use_focal=1, no_use_warp=2, use_pred=4, use_gt=8, pred_is_prob=16, loss=32, metrics=64, metrics_no_warp=128)
+FLAG = dict(use_focal=1, no_use_warp=2, use_pred=4, use_gt=8, pred_is_prob=16, loss=32, metrics=64, metrics_no_warp=128,
+            auc_float_labels=256)
 OUT_FLOATS = 19
 
 
@@ -147,11 +148,14 @@ class OGMFlow_loss:
 
 
 def compute_occupancy_flow_metrics(config, true_waypoints: WaypointGrids, pred_waypoints: WaypointGrids,
-                                   no_warp: bool = False):
-    """occu_metric.py:26-140.  `pred_waypoints` holds occupancy PROBABILITIES (train.py:142-154)."""
+                                   no_warp: bool = False, auc_float_labels: bool = False):
+    """occu_metric.py:26-140.  `pred_waypoints` holds occupancy PROBABILITIES (train.py:142-154).
+    `auc_float_labels`: tf.keras 2.6 / 2.7 AUC semantics (labels kept as floats) instead of the bool cast of every
+    other tf.keras version; only vehicles_flow_warped_occupancy_auc can differ (SJ_EVAL_AUC_FLOAT_LABELS)."""
     pred = pack_predictions(pred_waypoints)
     out = _run(pred, *pack_truth(true_waypoints, pred.device),
-               FLAG["metrics"] | FLAG["pred_is_prob"] | (FLAG["metrics_no_warp"] if no_warp else 0))
+               FLAG["metrics"] | FLAG["pred_is_prob"] | (FLAG["metrics_no_warp"] if no_warp else 0)
+               | (FLAG["auc_float_labels"] if auc_float_labels else 0))
     return _metrics_object(out, no_warp)
 
 
@@ -165,11 +169,12 @@ def _metrics_object(out: Tensor, no_warp: bool):
 
 
 def evaluate(pred_logits: Tensor, gt_obs: Tensor, gt_occ: Tensor, gt_flow: Tensor, origin: Tensor,
-             loss: Optional[OGMFlow_loss] = None, no_warp: bool = False):
+             loss: Optional[OGMFlow_loss] = None, no_warp: bool = False, auc_float_labels: bool = False):
     """val_step (train.py:252-283) in one pass: the model's logits [B,H,W,32] -> (loss dict, metrics object)."""
     loss = loss or OGMFlow_loss()
     out = _run(pred_logits, gt_obs, gt_occ, gt_flow, origin,
-               loss.flags() | FLAG["loss"] | FLAG["metrics"] | (FLAG["metrics_no_warp"] if no_warp else 0), loss.ogm_weight,
+               loss.flags() | FLAG["loss"] | FLAG["metrics"] | (FLAG["metrics_no_warp"] if no_warp else 0)
+               | (FLAG["auc_float_labels"] if auc_float_labels else 0), loss.ogm_weight,
                loss.occ_weight, loss.flow_origin_weight, loss.replica)
     d = {n: out[i] for i, n in enumerate(LOSS_NAMES)}
     if loss.no_use_warp:

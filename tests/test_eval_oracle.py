@@ -113,3 +113,23 @@ def test_eval_oracle_matches_golden(golden_dir):
         np.testing.assert_allclose(got, g[f"loss_{name}"], rtol=2e-5)
     m = E.occupancy_flow_metrics(**d)
     np.testing.assert_allclose(np.array([v.item() for v in m.values()]), g["metrics"], rtol=2e-5)
+
+
+def test_pr_auc_float_label_semantics():
+    """tf.keras 2.6 / 2.7 keep y_true as a float in the evenly-spaced-threshold update: identical to the bool cast for 0/1
+    labels, a mass-weighted confusion matrix otherwise (hand-worked: two samples, one threshold region)."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    y = (rng.random(500) < 0.3).astype(np.float32)
+    p = np.clip(0.6 * y + rng.normal(0.2, 0.25, 500), 0, 1).astype(np.float32)
+    a = E.keras_pr_auc(torch.from_numpy(y), torch.from_numpy(p)).item()
+    b = E.keras_pr_auc(torch.from_numpy(y), torch.from_numpy(p), float_labels=True).item()
+    assert abs(a - b) < 1e-6
+    # fractional labels: label 0.25 at prediction 0.9, label 0.0 at prediction 0.1
+    yt, yp = torch.tensor([0.25, 0.0]), torch.tensor([0.9, 0.1])
+    thr = torch.from_numpy(E.auc_thresholds())
+    above = (yp[None] > thr[:, None]).float()
+    tp, fp = (above * yt).sum(1), (above * (1 - yt)).sum(1)
+    want = E.interpolate_pr_auc(tp, fp, yt.sum() - tp).item()
+    got = E.keras_pr_auc(yt, yp, float_labels=True).item()
+    assert abs(got - want) < 1e-7
+    assert abs(got - E.keras_pr_auc(yt, yp).item()) > 0.05  # the bool cast counts the 0.25 label as a full positive

@@ -54,6 +54,21 @@ def test_metrics_and_fused_eval_parity(B, H, no_warp):
     assert torch.equal(loss["res"].cpu(), ref_l["res"])
 
 
+@pytest.mark.parametrize("B,H", [(2, 256), (16, 256)])
+def test_metrics_auc_float_label_semantics(B, H):
+    """SJ_EVAL_AUC_FLOAT_LABELS (tf.keras 2.6 / 2.7): labels keep their float value.  The warped-occupancy AUC -- whose
+    label is the fractional flow-grounded prediction -- changes, every binary-label metric stays put."""
+    from strajnet_b200 import evaluation as V
+    d = E.make_eval_inputs(B, H, seed=4)
+    ref_bool = E.occupancy_flow_metrics(**d)
+    ref_float = E.occupancy_flow_metrics(**d, auc_float_labels=True)
+    _, m = V.evaluate(**{("pred_logits" if k == "pred" else k): v for k, v in _cuda(d).items()}, auc_float_labels=True)
+    for k in V.METRIC_NAMES:
+        _close(getattr(m, k), ref_float[k], k + " (float labels)")
+    assert abs(float(ref_float["vehicles_observed_auc"]) - float(ref_bool["vehicles_observed_auc"])) < 1e-6
+    assert abs(float(ref_float["vehicles_flow_warped_occupancy_auc"]) - float(ref_bool["vehicles_flow_warped_occupancy_auc"])) > 1e-3
+
+
 def test_reference_call_surface_and_edge_cases():
     """The reference's own calling convention (train.py:103-154, 252-283): WaypointGrids of per-waypoint tensors, logits
     for the loss, probabilities for the metrics; empty scene -> divide_no_nan zeros; every gate off -> NaN flow loss."""

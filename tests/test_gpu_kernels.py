@@ -330,3 +330,39 @@ def test_tc_mlp96_tight(env):
     tol = REL * ref.abs() + 4e-3   # + tanh.approx (2^-11) through fc2 and rounding-tie flips of the bf16 hidden tile
     print(f"tc_mlp96: max |err| {err.max().item():.3e}")
     assert (err <= tol).all(), f"tc_mlp96: max excess {(err - tol).max().item():.3e}"
+
+
+@pytest.mark.parametrize("B,inplace", [(3, False), (5, True)])
+def test_res_add2_fused_tight(env, B, inplace):
+    """tc_resadd2: both 64x64 skip connections (res_layer[1] on res0, res_f on flow_res) in one kernel, against fp32 torch
+    on the same bf16 operands with the same two rounding points (x stored as bf16, fx = stored x + ...).  B = 3 / 5 give
+    the 18 CTAs of a waypoint uneven tile counts; the in-place form (dst_a aliasing src) is what the decoder uses."""
+    _lib, weights, dev = env
+    lib = _lib.lib()
+    HW, Cin, Cout = 4096, 96, 128
+    ka = randn((8, 1, 1, Cin, Cout), 71, (6.0 / (8 * Cin + 8 * Cout)) ** 0.5)
+    kb = randn((8, 1, 1, Cin, Cout), 72, (6.0 / (8 * Cin + 8 * Cout)) ** 0.5)
+    ba, bb = randn((Cout,), 73, 0.1), randn((Cout,), 74, 0.1)
+    pa = weights.Packer({"kernel": ka, "bias": ba}, dev, tc=True)
+    pb = weights.Packer({"kernel": kb, "bias": bb}, dev, tc=True)
+    la, lb = pa._res(""), pb._res("")
+    sa, sb = _bf(randn((B, HW, Cin), 75)), _bf(randn((B, HW, Cin), 76))
+    src = _bf(randn((B, 8, HW, Cout), 77))
+    sad, sbd, srcd = (t.to(dev, torch.bfloat16) for t in (sa, sb, src))
+    dst_a = srcd if inplace else torch.empty_like(srcd)
+    dst_b = torch.empty_like(srcd)
+    lib.sj_tc_launch_count(1)
+    _lib.check(lib.sj_res_add2_fwd(sad.data_ptr(), sbd.data_ptr(), srcd.data_ptr(), dst_a.data_ptr(), dst_b.data_ptr(),
+                                   C.byref(la), C.byref(lb), B, HW, Cin, Cout, _lib.SJ_BF16, _stream()), "res_add2")
+    torch.cuda.synchronize()
+    assert lib.sj_tc_launch_count(1) == 1, "the fused skip-add kernel did not run"
+    wa, wb = _bf(weights.collapse_conv3d_811(ka)), _bf(weights.collapse_conv3d_811(kb))
+    ref_a = src + O.elu(torch.einsum("bnc,tcd->btnd", sa, wa) + ba)
+    ya = dst_a.float().cpu()
+    ex = (ya - ref_a).abs() - (REL * ref_a.abs() + ABS)
+    assert ex.max().item() <= 0, f"res_add2 x: exceeds one output rounding by {ex.max().item():.3e}"
+    # the flow branch adds onto the STORED x (bf16), exactly as two separate launches would
+    ref_b = ya + O.elu(torch.einsum("bnc,tcd->btnd", sb, wb) + bb)
+    yb = dst_b.float().cpu()
+    ex = (yb - ref_b).abs() - (REL * ref_b.abs() + ABS)
+    assert ex.max().item() <= 0, f"res_add2 fx: exceeds one output rounding by {ex.max().item():.3e}"
