@@ -26,11 +26,14 @@ constexpr int TH = 16, TW = 8, PH = TH + 1, PW = TW + 1;
 constexpr int NTHREADS = 320;
 constexpr int A_SUB = (PH * PW * KC * 2 + 1023) & ~1023;  // 19584 -> 20480 B
 constexpr int A_SLOT = NCH * A_SUB;                       // 40 KB
-constexpr int NA = 3;
+constexpr int NA = 2;                                     // (3 before the output staging buffer took 28 KB)
 constexpr int B_TILE = COUT * KC * 2;                     // 12 KB: [96 rows][128 B]
 constexpr int B_BYTES = NCH * 4 * B_TILE;                 // 96 KB
+constexpr int STG_ROW = 112;                              // 96 bytes of one pixel (48 channels) + 16: conflict-free rows
+constexpr int STG_WARP = 32 * STG_ROW;                    // 3.5 KB per epilogue warp
 constexpr int OFF_B = NA * A_SLOT;
-constexpr int OFF_BAR = OFF_B + B_BYTES;
+constexpr int OFF_STG = OFF_B + B_BYTES;
+constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
 constexpr int SMEM_BYTES = OFF_BAR + 1024;
 constexpr int NACC = 4, ACC_COLS = 128;                   // accumulator stages (96 columns used of each 128)
 
@@ -145,22 +148,36 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     float bias_r[COUT / 2];  // this thread's 48 output channels never change: bias lives in registers
 #pragma unroll
     for (int i = 0; i < COUT / 2; ++i) bias_r[i] = bias_s[c0 + i];
+    // Output rows leave through a per-warp shared-memory transpose: a thread's 96 bytes (its pixel, 48 channels) are 384
+    // bytes away from its neighbour's in global memory, so direct 16-byte stores cost 32 L1 wavefronts per instruction;
+    // after the transpose six consecutive lanes cover one pixel's 96 bytes (6-8 wavefronts per instruction).
+    uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_WARP;
+    int s_off[6], g_off[6];  // piece g = 32 i + lane of the warp's 32 x 6 sixteen-byte pieces: pixel g / 6, piece g % 6
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int g = 32 * i + lane, pix = g / 6, pc = g % 6;
+      const int pty = quarter * 4 + pix / TW, ptx = pix % TW;  // tile coordinates of that pixel
+      s_off[i] = pix * STG_ROW + pc * 16;
+      g_off[i] = ((2 * pty) * (2 * p.W) + 2 * ptx) * COUT * 2 + pc * 16;  // bytes from the tile's first output pixel
+    }
     int acc = 0;
     uint32_t tph = 0;
     for (int t = t_first; t < p.num_tiles; t += t_step) {
       const int n = t / tiles_per_img, tr = t % tiles_per_img;
-      const int yy = (tr / p.tiles_x) * TH + ty, xx = (tr % p.tiles_x) * TW + tx;
+      const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;
       mbar_wait(&tfull[acc], tph);
       tc_fence_after();
-      bf16* dst = p.out + (((long long)n * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px) * COUT + c0;
+      uint8_t* tile0 = reinterpret_cast<uint8_t*>(
+          p.out + (((long long)n * (2 * p.H) + 2 * y0 + py) * (2 * p.W) + 2 * x0 + px) * COUT + c0);
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_COLS + c0;
+      uint4* row = reinterpret_cast<uint4*>(stg + lane * STG_ROW);
       {
         float v[32];
         tmem_ld32(t_addr, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i] + bias_r[i], ACT_ELU);
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) st8_bf16(dst + i, v + i);
+        for (int i = 0; i < 32; i += 8) st8_bf16(reinterpret_cast<bf16*>(row + i / 8), v + i);
       }
       {
         float v[16];
@@ -168,11 +185,15 @@ tc_upconv1p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i] + bias_r[32 + i], ACT_ELU);
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) st8_bf16(dst + 32 + i, v + i);
+        for (int i = 0; i < 16; i += 8) st8_bf16(reinterpret_cast<bf16*>(row + 4 + i / 8), v + i);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is drained: the stores below overlap the next MMAs
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        *reinterpret_cast<uint4*>(tile0 + g_off[i]) = *reinterpret_cast<const uint4*>(stg + s_off[i]);
+      __syncwarp();
       if (++acc == NACC) { acc = 0; tph ^= 1; }
     }
   }
