@@ -47,20 +47,47 @@ __global__ void __launch_bounds__(NTHREADS, 4) head_tapsum_kernel(const HeadSumP
   pdl_wait();
   pdl_trigger();
 
+  // Loader: the 16-byte pieces of a halo tile are dealt to the threads once (piece tid + 256 k -> row, column), so that a
+  // sub-item costs each thread four address adds and four cp.async; validity (image border) changes only with the item.
+  constexpr int NPIECE = (TH + 2) * ROW_CHUNKS, KMAX = (NPIECE + NTHREADS - 1) / NTHREADS;
+  int p_soff[KMAX], p_row[KMAX], p_col[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int c = tid + k * NTHREADS;
+    p_row[k] = c < NPIECE ? c / ROW_CHUNKS : -100000;  // never valid
+    p_col[k] = (c % ROW_CHUNKS) * 16;
+    p_soff[k] = (c / ROW_CHUNKS) * SROW + p_col[k];
+  }
+  int l_item = -1;
+  int l_goff[KMAX];  // byte offset inside one [256,256,18] image
+  unsigned l_ok = 0;
+  long long l_img0 = 0;
   auto load = [&](int s) {
     if (s < total) {
       const int item = blockIdx.x + (s >> 4) * gridDim.x, th = s & 15;
-      const int b = item / TILES_PER_IMG, tr = item % TILES_PER_IMG;
-      const int y0 = (tr / TILES_X) * TH, x0 = (tr % TILES_X) * TW;
-      const uint8_t* img = p.z[th & 1] + (long long)(b * 8 + (th >> 1)) * 256 * ROW_B;
-      const uint32_t dst0 = smem_base + (s % NST) * STAGE;
-      const int col0 = x0 * PIX_B - PIX_B - LEAD;  // 16-byte aligned (x0 is a multiple of 32)
-      for (int c = tid; c < (TH + 2) * ROW_CHUNKS; c += NTHREADS) {
-        const int row = c / ROW_CHUNKS, col = c % ROW_CHUNKS;
-        const int y = y0 - 1 + row, off = col0 + col * 16;
-        const bool ok = y >= 0 && y < 256 && off >= 0 && off < ROW_B;
-        cp_async16(dst0 + row * SROW + col * 16, ok ? img + (long long)y * ROW_B + off : p.z[0], ok ? 16 : 0);
+      if (item != l_item) {  // new tile: origin, validity of this thread's pieces
+        l_item = item;
+        const int b = item / TILES_PER_IMG, tr = item % TILES_PER_IMG;
+        const int y0 = (tr / TILES_X) * TH, x0 = (tr % TILES_X) * TW;
+        const int col0 = x0 * PIX_B - PIX_B - LEAD;  // 16-byte aligned (x0 is a multiple of 32)
+        l_img0 = (long long)b * 8 * 256 * ROW_B;
+        l_ok = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int y = y0 - 1 + p_row[k], off = col0 + p_col[k];
+          const bool ok = y >= 0 && y < 256 && off >= 0 && off < ROW_B;
+          l_ok |= (ok ? 1u : 0u) << k;
+          l_goff[k] = y * ROW_B + off;
+        }
       }
+      const uint8_t* img = p.z[th & 1] + l_img0 + (long long)(th >> 1) * 256 * ROW_B;
+      const uint32_t dst0 = smem_base + (s % NST) * STAGE;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (p_row[k] >= 0) {
+          const bool ok = (l_ok >> k) & 1;
+          cp_async16(dst0 + p_soff[k], ok ? img + l_goff[k] : p.z[0], ok ? 16 : 0);
+        }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };

@@ -82,6 +82,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(bars + 48);  // [Cout] (<= 256 floats), 16-byte aligned
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(bars) + 2048;  // 8 epilogue warps x 2 KB output staging (see the epilogue)
   for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) bias_s[i] = p.bias[i];
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
@@ -243,16 +244,36 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {
     const int quarter = warp % 4, px = (warp - 2) / 4;  // warps 2..5 -> px 0, warps 6..9 -> px 1
     const int r = quarter * 32 + lane, ty = r / TW, tx = r % TW;
+    // Output rows leave through a per-warp shared-memory transpose, 32 channels at a time: a thread's pixel is 2 * Cout * 2
+    // bytes away from its neighbour's in global memory, so direct 16-byte stores cost 32 L1 wavefronts per instruction;
+    // after the transpose four consecutive lanes cover one pixel's 64 bytes (8 wavefronts per instruction).
+    uint8_t* stg = stg_all + (warp - 2) * 2048;
     int acc = 0;
     uint32_t tph = 0;
     for (int t = cta_in_phase; t < p.num_tiles; t += ctas_per_phase) {
       const int n = t / tiles_per_img, tr = t % tiles_per_img;
-      const int yy = (tr / p.tiles_x) * TH + ty, xx = (tr % p.tiles_x) * TW + tx;
+      const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;
       mbar_wait(&tfull_bar[acc], tph);
       tc_fence_after();
       {
-        bf16* dst = p.out + (((long long)n * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px) * p.Cout;
+        // first output pixel of this warp's four tile rows
+        bf16* warp0 = p.out + (((long long)n * (2 * p.H) + 2 * (y0 + quarter * 4) + py) * (2 * p.W) + 2 * x0 + px) * p.Cout;
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * 2 + px) * p.acs;
+        auto flush = [&](int c, int cnt) {  // cnt = 32 or 16 channels staged at [lane][cnt * 2 bytes]
+          __syncwarp();
+          const int per = cnt / 8;  // 16-byte pieces per pixel
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int g = 32 * i + lane;
+            if (g < 32 * per) {
+              const int pix = g / per, pc = g % per;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + pix * 64 + ((pc ^ ((pix >> 1) & 3)) << 4));
+              bf16* d = warp0 + ((long long)(2 * (pix / TW)) * (2 * p.W) + 2 * (pix % TW)) * p.Cout + c + pc * 8;
+              *reinterpret_cast<uint4*>(d) = v;
+            }
+          }
+          __syncwarp();
+        };
         int c = 0;
         for (; c + 32 <= p.Cout; c += 32) {
           float v[32];
@@ -264,7 +285,9 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
           }
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) st8_bf16(dst + c + i, v + i);
+          for (int i = 0; i < 32; i += 8)
+            st8_bf16(reinterpret_cast<bf16*>(stg + lane * 64 + (((i / 8) ^ ((lane >> 1) & 3)) << 4)), v + i);
+          flush(c, 32);
         }
         if (c < p.Cout) {
           float v[16];
@@ -276,7 +299,9 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             v[i + 2] = act_fast(v[i + 2] + b4.z, ACT_ELU); v[i + 3] = act_fast(v[i + 3] + b4.w, ACT_ELU);
           }
 #pragma unroll
-          for (int i = 0; i < 16; i += 8) st8_bf16(dst + c + i, v + i);
+          for (int i = 0; i < 16; i += 8)
+            st8_bf16(reinterpret_cast<bf16*>(stg + lane * 64 + (((i / 8) ^ ((lane >> 1) & 3)) << 4)), v + i);
+          flush(c, 16);
         }
       }
       tc_fence_before();
@@ -313,7 +338,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   p.a_slot = ANCH * p.a_sub;
   p.na = 3;
   const int b_sub = p.Cout * rowb;
-  const int budget = 222 * 1024 - 1024 - 2048;  // alignment slack + barriers + bias
+  const int budget = 222 * 1024 - 1024 - 2048 - 16384;  // alignment slack + barriers + bias + output staging
   int b_bytes;
   if (RESB) {
     b_bytes = 8 * NCH * b_sub;
@@ -325,7 +350,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
     if (p.nbs < 2) { c.fail(SJ_EUNSUPPORTED); return; }
     b_bytes = p.nbs * b_stage;
   }
-  size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 2048;  // barriers + bias
+  size_t smem = 1024 + (size_t)p.na * p.a_slot + ((b_bytes + 1023) & ~1023) + 2048 + 16384;  // barriers + bias + staging
   if (smem > 227 * 1024) { c.fail(SJ_EUNSUPPORTED); return; }
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   if (!SJ_SMEM_LIMIT_OK((tc_upconv_kernel<KC, NCH, RESB, A128>), 227 * 1024)) {

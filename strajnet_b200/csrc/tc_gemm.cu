@@ -49,6 +49,8 @@ struct KParams {
   float* st_mean;  // optional: LayerNorm statistics of the OUTPUT rows (needs BN == N), written at the C row index
   float* st_rstd;
   float st_eps;
+  int coal;       // output rows of a tile are consecutive in C: store through the per-warp transpose (see the epilogue)
+  int stg_off;    // byte offset of the staging buffers from the barrier block
   int a_rows;     // rows per A stage (128; 256 for the shifted-view probe)
   int dbg_shift;  // probe: the MMA reads A rows [shift, shift+128) of the stage
   int dbg_bo;     // probe: set the descriptor base_offset field from the start address
@@ -178,6 +180,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       asm volatile("bar.sync 5, %0;" ::"n"(EW * 32) : "memory");
     }
+    // Coalesced stores: thread r owns output row r, whose neighbour rows are ldc * 2 bytes away, so a direct 16-byte store
+    // per thread costs 32 L1 wavefronts per instruction (measured: the LSU wavefront pipe was the busiest unit of the
+    // store-heavy GEMMs).  When the rows of a tile are consecutive in C, each 32-column chunk goes through a 2 KB per-warp
+    // transpose instead and four consecutive lanes write one row's 64 bytes (8 wavefronts per instruction).
+    uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + p.stg_off + (warp - 2) * 2048;
     int as = 0;
     uint32_t aphase = 0;
     // output row of this thread in a tile: validity, C/R row index (after the row maps), group, first column
@@ -265,7 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int i = 0; i < CNT / 8; ++i) rr[i] = rn[4 * CI + i];
           if (nvalid) prefetch(CI, ncrow, nn0);  // this chunk's registers are free again: fetch the next tile's
         }
-        if (!valid) return;
+        if (!valid && !p.coal) return;
 #pragma unroll
         for (int i = 0; i < CNT; i += 4) {  // 16-byte loads of the per-column vectors (L1-resident)
           float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = l4;
@@ -280,7 +287,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
 #pragma unroll
         for (int i = 0; i < CNT; i += 8) {
-          if (p.R) {
+          if (p.R && valid) {
             const uint32_t w[4] = {rr[i / 8].x, rr[i / 8].y, rr[i / 8].z, rr[i / 8].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -296,7 +303,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               st_q = fmaf(r, r, st_q);
             }
           }
-          st8_bf16(p.C + crow * p.ldc + n + i, v + i);
+          if (p.coal) st8_bf16(reinterpret_cast<bf16*>(stg + lane * 64 + (((i / 8) ^ ((lane >> 1) & 3)) << 4)), v + i);
+          else st8_bf16(p.C + crow * p.ldc + n + i, v + i);
+        }
+        if (p.coal) {
+          constexpr int PER = CNT / 8;  // 16-byte pieces per row in this chunk
+          __syncwarp();
+          const long long crow0 = __shfl_sync(0xffffffffu, crow, 0);  // lane 0 of a warp with any valid row is valid
+          const int rows_ok = min(32, p.M - (m - lane));               // valid rows of this warp
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int gidx = 32 * i + lane, row = gidx / PER, pc = gidx % PER;
+            if (row < rows_ok) {
+              const uint4 o = *reinterpret_cast<const uint4*>(stg + row * 64 + ((pc ^ ((row >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(p.C + (crow0 + row) * p.ldc + n + pc * 8) = o;
+            }
+          }
+          __syncwarp();
         }
       };
       if constexpr (RPF) {
@@ -463,17 +486,32 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     c.fail(SJ_ECUDA);
     return;
   }
-  size_t smem = 1024 + (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2) + 256 + 2 * 4 * BM * sizeof(float2);
+  // Two experiment knobs, both measured neutral on B200 at batch 16 (DESIGN.md 5) and therefore off by default:
+  // SJ_TCG_EW=16: 16 epilogue warps (4 per TMEM lane quarter; needs >= 16 columns per warp);
+  // SJ_TCG_RPF=1: the residual-prefetch epilogue (145+ registers: 8 warps only).
+  static const bool ew16_on = getenv("SJ_TCG_EW") != nullptr && atoi(getenv("SJ_TCG_EW")) == 16;
+  static const bool rpf_on = getenv("SJ_TCG_RPF") != nullptr;
+  const bool ew16 = ew16_on && p.BN >= 64;
+  const size_t ring = (size_t)STAGES * (p.a_rows * BK * 2 + p.BN * BK * 2);
+  size_t tail = 256 + 2 * 4 * BM * sizeof(float2);  // barriers, output-statistics partials
+  // rows of a tile consecutive in C <=> no scatter map and the [outer][G][inner] interleave (if any) is tile-aligned
+  static const bool coal_off = getenv("SJ_TCG_NO_COALESCE") != nullptr;
+  const size_t staging = (size_t)(ew16 ? 16 : 8) * 2048;
+  p.coal = !coal_off && !a.cm.map && (a.cm.inner == 0 || a.cm.inner % BM == 0) && a.ldc % 8 == 0 &&
+           1024 + ring + tail + staging <= 227 * 1024;
   {
     // stage the per-column vectors when they are dense ([groups][N]) and fit beside the operand ring
     const int vec = p.groups * a.N;
     const bool dense = (p.groups == 1 || ((!a.bias || a.bias_gstride == a.N) && (!a.ln_mean || a.ln_gstride == a.N)));
     const size_t need = (size_t)vec * 4 * (a.ln_mean ? 2 : 1);
-    if ((a.bias || a.ln_mean) && dense && smem + need <= 225 * 1024 && need <= 24 * 1024) {
+    if ((a.bias || a.ln_mean) && dense && 1024 + ring + tail + need + (p.coal ? staging : 0) <= 225 * 1024 && need <= 24 * 1024) {
       p.vec_smem = vec;
-      smem += need;
+      tail += need;
     }
   }
+  tail = (tail + 15) & ~size_t(15);
+  p.stg_off = (int)tail;
+  const size_t smem = 1024 + ring + tail + (p.coal ? staging : 0);
   const int tiles = p.m_tiles * p.n_tiles * p.groups;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // at least ~115 KB so that two CTAs (each allocating all 512 TMEM columns) can never share an SM
@@ -487,12 +525,6 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
     }                                                                                                                 \
     SJ_LAUNCH(c, "tc_gemm", (tc_gemm_kernel<ACT_, LN_, RPF_, EW_>), grid, nthreads(EW_), smem_launch, mapA, mapB, p); \
   } while (0)
-  // Two experiment knobs, both measured neutral on B200 at batch 16 (DESIGN.md 5) and therefore off by default:
-  // SJ_TCG_EW=16: 16 epilogue warps (4 per TMEM lane quarter; needs >= 16 columns per warp);
-  // SJ_TCG_RPF=1: the residual-prefetch epilogue (145+ registers: 8 warps only).
-  static const bool ew16_on = getenv("SJ_TCG_EW") != nullptr && atoi(getenv("SJ_TCG_EW")) == 16;
-  static const bool rpf_on = getenv("SJ_TCG_RPF") != nullptr;
-  const bool ew16 = ew16_on && p.BN >= 64;
 #define SJ_TCG(ACT_, LN_, RPF_)                    \
   do {                                             \
     if (ew16 && !(RPF_)) SJ_TCG2(ACT_, LN_, false, 16); \
