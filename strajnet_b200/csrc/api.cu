@@ -17,7 +17,7 @@ static int g_pdl = -1;  // -1: not decided yet (environment); else bit 0 = tcgen
 int pdl_mask() {
   if (g_pdl < 0) {
     const char* m = getenv("SJ_PDL_MASK");
-    g_pdl = getenv("SJ_NO_PDL") ? 0 : (m ? atoi(m) & 3 : 0);
+    g_pdl = getenv("SJ_NO_PDL") ? 0 : (m ? atoi(m) & 7 : 0);
   }
   return g_pdl;
 }
@@ -812,7 +812,7 @@ long long sj_launch_count(int reset) {
 
 int sj_set_pdl(int on) {
   const int prev = sj::pdl_mask();
-  if (on >= 0) sj::g_pdl = on & 3;
+  if (on >= 0) sj::g_pdl = on & 7;
   return prev;
 }
 long long sj_tc_launch_count(int reset) {

@@ -81,11 +81,11 @@ void probe_after(Ctx& c, int slot);
 // SJ_PDL_MASK).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// which launches get the attribute: bit 0 = tcgen05 kernels ("tc_*"), bit 1 = all others
+// which launches get the attribute: bit 0 = tcgen05 kernels ("tc_*"), bit 1 = all others, bit 2 = front half of the forward only
 int pdl_mask();
 
 template <typename... Exp, typename... Act>
-inline void launch_kernel(const char* what, cudaStream_t stream, dim3 grid, dim3 block, size_t smem,
+inline void launch_kernel(const char* what, const char* role, cudaStream_t stream, dim3 grid, dim3 block, size_t smem,
                           void (*kernel)(Exp...), Act&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -97,7 +97,13 @@ inline void launch_kernel(const char* what, cudaStream_t stream, dim3 grid, dim3
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   const bool is_tc = what[0] == 't' && what[1] == 'c' && what[2] == '_';
-  cfg.numAttrs = (pdl_mask() & (is_tc ? 1 : 2)) ? 1 : 0;
+  // bit 2 of the mask restricts programmatic launches to the latency-bound front half of the forward (encoder, FG-MSA,
+  // trajectory stack: ~75 launches of a few microseconds each); the decoder's long persistent kernels lose from early-
+  // resident successors holding shared memory / TMEM slots
+  const int mask = pdl_mask();
+  bool front = true;
+  if (mask & 4) front = role && (role[0] == 'e' || role[0] == 'f' || role[0] == 't');  // "enc", "fgmsa", "traj*"
+  cfg.numAttrs = ((mask & (is_tc ? 1 : 2)) && front) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);
 }
 
@@ -120,7 +126,7 @@ inline void launch_kernel(const char* what, cudaStream_t stream, dim3 grid, dim3
   do {                                                                                        \
     if (!(ctx).dry && (ctx).ok()) {                                                           \
       int sj_slot_ = sj::probe_before(ctx);                                                   \
-      sj::launch_kernel(what, (ctx).stream, dim3(grid), dim3(block), (smem), kernel, __VA_ARGS__);  \
+      sj::launch_kernel(what, (ctx).role, (ctx).stream, dim3(grid), dim3(block), (smem), kernel, __VA_ARGS__);  \
       sj::probe_after((ctx), sj_slot_);                                                       \
       sj::note_launch((ctx), what);                                                           \
     }                                                                                         \
