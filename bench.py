@@ -275,6 +275,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {}
+    if world > 1 and os.environ.get("SJ_NO_NUMA_BIND") is None:
+        from strajnet_b200.parallel import bind_to_local_numa
+        numa = bind_to_local_numa(local)  # before any pinned allocation: staging buffers land on the GPU's own node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
@@ -505,6 +509,8 @@ def main():
         }
         if dp is not None:
             line.update(dp)
+        if numa:
+            line["host_binding"] = numa
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

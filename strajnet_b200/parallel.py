@@ -13,6 +13,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_local_numa(device_index: int) -> dict:
+    """Pin this process (and with it the first-touch placement of its pinned host buffers) to the CPUs of the NUMA node
+    the GPU hangs off.  With one process per GPU on a two-socket box, pinned staging buffers otherwise land wherever the
+    launcher started the process, and every host<->device copy of half the ranks crosses the socket interconnect.
+    Call before allocating pinned memory.  Best effort: returns {} when sysfs does not say."""
+    import os
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": bdf}
+    except (OSError, ValueError, AttributeError):
+        return {}
+
+
 def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous sample range [lo, hi) of `rank`; the global batch must divide evenly (all-gather needs equal shards)."""
     if world <= 0 or not (0 <= rank < world):
