@@ -17,7 +17,9 @@
  *     model inputs (rasters, actors) are always fp32; weights are fp32 ([in,out] Keras layout)
  *     with an optional bf16 tensor-core copy (`w_tc`, [out,in] K-major) used when dtype==SJ_BF16;
  *   - stream-ordered and asynchronous: no host sync, no allocation, no global mutable state that results depend on;
- *     the caller owns all buffers including `workspace`; safe to capture in a CUDA graph;
+ *     the caller owns all buffers including `workspace`; safe to capture in a CUDA graph.  The whole-model forward forks
+ *     the trajectory actor branch onto ONE helper stream per host thread and device (created lazily together with two
+ *     events, joined before the branch's results are used: the caller sees plain stream order);
  *   - return 0 (SJ_OK) or a negative SjStatus; never throws.
  *
  * Process-level knobs (none of them changes a result beyond the documented bf16 tolerance; all are opt-in):
@@ -27,7 +29,7 @@
  *     its replacement (each selects between two implementations of the same op): SJ_DISABLE_FUSED_WMSA,
  *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION, SJ_DISABLE_RESADD2, SJ_DISABLE_LOCKSTEP,
  *     SJ_DISABLE_ATTN_MMA, SJ_DISABLE_IM2COL_STAGED, SJ_DISABLE_NORM_FAST, SJ_DISABLE_FG_OFFSET_MMA (fall back to the
- *     previous kernel), SJ_SIDE_STREAM (actor branch on a helper stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue
+ *     previous kernel), SJ_NO_SIDE_STREAM (keep the trajectory actor branch on the caller's stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue
  *     variants), SJ_NO_PDL (forces the PDL mask to 0).
  */
 #ifndef STRAJNET_B200_H_

@@ -645,13 +645,13 @@ void strajnet_impl(Ctx& c, const void* ogm, const void* map_img, const float* fl
   void* res2 = c.alloc_act((size_t)B * 256 * 384);
   void* query = c.alloc_act((size_t)B * 2048 * 384);
   void* obs_value = c.alloc_act((size_t)B * 2048 * 384);
-  // The actor branch of the trajectory stack (TrajNet: ~15 small latency-bound launches) depends on obs / occ only and
-  // can be forked onto a helper stream beside the raster encoder (join = event wait: still asynchronous and CUDA-graph
-  // capturable).  Opt-in (SJ_SIDE_STREAM=1): measured on B200 it LOSES 2 % at batch 16 (3.61 vs 3.52 ms) -- the
-  // encoder's kernels are persistent one-CTA-per-SM grids, and a helper CTA squatting on an SM turns that SM's CTA
-  // into a straggler for the whole grid.
+  // The actor branch of the trajectory stack (TrajNet: ~15 small latency-bound launches, 120 us) depends on obs / occ only:
+  // it is forked onto a helper stream beside the patch embedding (join = event wait: still asynchronous and CUDA-graph
+  // capturable).  Measured on B200 at batch 16, three A/B pairs: 2.503 -> 2.444 ms per step (round 1 measured a 2 % LOSS:
+  // then the helper CTAs squatted beside one-CTA-per-SM persistent encoder grids; the encoder now starts with the
+  // non-persistent im2col / combine kernels and runs its 96-channel branches in lock step).  SJ_NO_SIDE_STREAM=1 disables.
   TrajActorBufs tb = traj_actor_alloc(c, B);
-  static const bool fork_on = getenv("SJ_SIDE_STREAM") != nullptr;
+  static const bool fork_on = getenv("SJ_NO_SIDE_STREAM") == nullptr;
   bool forked = false;
   if (!c.dry && c.ok() && fork_on && side_stream_ready()) {
     TlsState& t = tls();

@@ -37,7 +37,7 @@ def bind_to_local_numa(device_index: int) -> dict:
             return {}
         os.sched_setaffinity(0, allowed)
         return {"numa_node": node, "cpus": len(allowed), "pci": bdf}
-    except (OSError, ValueError, AttributeError):
+    except Exception:  # noqa: BLE001 -- no GPU, no sysfs, restricted affinity: leave the process where it is
         return {}
 
 

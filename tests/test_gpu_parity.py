@@ -494,3 +494,18 @@ def test_strajnet_bf16_error_profile(sj, name, B, S, large):
     assert flat.max().item() < 0.08 * rng
     assert flat.mean().item() < 2.5e-2 and p999 < 0.1
     assert rms_b < 1.6 * rms_i + 1e-3
+
+
+def test_inference_pipeline_stale_handle_raises(sj):
+    """A handle whose slot has been handed to a later submit() must not return that batch's data."""
+    from strajnet_b200.pipeline import InferencePipeline
+    m = _model(sj)
+    pipe = InferencePipeline(m, batch=1, depth=2)
+    b = {k: v.pin_memory() for k, v in O.make_inputs(1, 256, seed=40).items() if k != "mapt"}
+    h0 = pipe.submit(b)
+    h1 = pipe.submit(b)
+    h2 = pipe.submit(b)  # reuses h0's slot
+    with pytest.raises(RuntimeError):
+        h0.result()
+    assert torch.equal(h1.result(), h2.result())
+    pipe.synchronize()

@@ -138,3 +138,25 @@ def test_evaluation_host_logic():
     assert C.sizeof(L.SjEvalParams) == 20
     with pytest.raises(RuntimeError):
         OGMFlow_loss(None).packed(out, o, c, f, r)  # CPU tensors: the op runs on the GPU or raises
+
+
+def test_output_grid_answers_the_serving_loops_calls():
+    """inference.py:109-113 slices the model output, :130 applies an op to the slices, :169-181 calls .numpy() on them."""
+    import numpy as np
+    import torch
+    from strajnet_b200.layers import OutputGrid
+    y = torch.arange(2 * 4 * 4 * 32, dtype=torch.float32).reshape(2, 4, 4, 32).as_subclass(OutputGrid)
+    k = 3
+    wp = y[:, :, :, k * 4:(k + 1) * 4]
+    obs, flow = wp[:, :, :, :1], wp[:, :, :, 2:]
+    assert isinstance(obs, OutputGrid) and isinstance(torch.sigmoid(obs), OutputGrid)
+    a = torch.sigmoid(obs).numpy()
+    assert isinstance(a, np.ndarray) and a.shape == (2, 4, 4, 1)
+    q = np.clip(np.round(flow.numpy()), -128, 127).astype(np.int8)
+    assert q.shape == (2, 4, 4, 2)
+    assert np.asarray(wp).dtype == np.float32 and np.asarray(wp, dtype=np.float64).dtype == np.float64
+
+
+def test_numa_binding_is_best_effort():
+    from strajnet_b200.parallel import bind_to_local_numa
+    assert isinstance(bind_to_local_numa(0), dict)  # no GPU here: {} and no exception

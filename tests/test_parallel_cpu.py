@@ -76,3 +76,15 @@ def test_dp_gather_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_data_parallel_wrapper_defaults_and_validation():
+    """The wrapper is inference-only: training defaults to False (the model raises on True), and missing inputs are
+    reported before any sharding."""
+    import inspect
+    import pytest
+    from strajnet_b200.parallel import DataParallelSTrajNet
+    assert inspect.signature(DataParallelSTrajNet.__call__).parameters["training"].default is False
+    dp = DataParallelSTrajNet(model=lambda *a, **k: None)
+    with pytest.raises(ValueError):
+        dp(None, None, obs=None, occ=None, flow=None)
