@@ -327,10 +327,13 @@ def main():
     # over PCIe after its host-side casts.  The fp32-in / fp32-logits-out variant is reported beside it.
     # N > 1: the pipeline gathers the result grids of every step on every rank (its own side stream, copy engines).
     host_raw = dict(host)
-    host_raw["ogm"] = (host["ogm"] != 0).to(torch.uint8).pin_memory()
+    # the vehicle plane of the record's [S,S,11,2] raster is the only one the model reads (modules.py:572): the record
+    # decoder hands over that plane alone (records.decode_example(vehicle_plane_only=True))
+    host_raw["ogm"] = (host["ogm"][..., 0] != 0).to(torch.uint8).contiguous().pin_memory()
     host_raw["map_img"] = torch.round(host["map_img"] * 256).to(torch.int8).pin_memory()
     depth = int(os.environ.get("SJ_E2E_DEPTH", "2"))
-    pipes = {"raw": (InferencePipeline(model, B, depth=depth, raw_inputs=True, quantized=True, gather=world > 1), host_raw),
+    pipes = {"raw": (InferencePipeline(model, B, depth=depth, raw_inputs=True, quantized=True, gather=world > 1,
+                                       vehicle_plane_only=True), host_raw),
              "fp32": (InferencePipeline(model, B, depth=depth, gather=world > 1), host)}
     pipe, host_e2e = pipes["raw"]
     pending = []
@@ -499,7 +502,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "how": "InferencePipeline(raw_inputs, quantized): pinned host -> device (uint8 rasters, int8 map, fp32 flow/actors), forward, fused submission quantisation, device -> pinned host (uint8 grids) every "
+                    "how": "InferencePipeline(raw_inputs, quantized, vehicle_plane_only): pinned host -> device (uint8 vehicle-plane raster [B,S,S,11], int8 map, fp32 flow/actors), forward, fused submission quantisation, device -> pinned host (uint8 grids) every "
                            "step; 3 streams, double-buffered; synchronised wall clock, max over ranks"
                            + (f"; every step's uint8 grids all-gathered on every rank ({e2e_gather})" if world > 1 else ""),
                     "fp32_io": {"value": world * B * args.steps / (ms_e2e_fp32 / 1e3), "unit": UNIT,

@@ -301,7 +301,13 @@ int sj_decoder_tail_fwd(const void* x3, const void* f3, void* out, const SjDecod
  * decoder head: out is uint8 [B,256,256,32], channel k*4+{0,1} = round(sigmoid(logit)*255) as uint8, k*4+{2,3} =
  * clip(round(flow),-128,127) as int8. */
 typedef enum { SJ_IN_F32 = 0, SJ_IN_U8 = 1, SJ_IN_I8_DIV256 = 2 } SjInputType;
-typedef struct { int ogm_type; int map_type; int out_mode; } SjIoSpec;
+typedef struct {
+  int ogm_type;   /* SJ_IN_F32 or SJ_IN_U8 */
+  int map_type;   /* SJ_IN_F32 or SJ_IN_I8_DIV256 */
+  int out_mode;   /* 0: fp32 logits, 1: quantised submission bytes */
+  int ogm_planes; /* 2: the record's [B,S,S,11,2] raster (the model reads plane 0 only, modules.py:572);
+                     1: the caller hands over that plane alone, [B,S,S,11] (half the host->device bytes of the largest input) */
+} SjIoSpec;
 int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, const float* obs, const float* occ,
                        void* out, const SjModelW* w, const SjIoSpec* io, int B, int S, int dtype, void* workspace,
                        size_t workspace_bytes, sj_stream_t stream);

@@ -73,7 +73,7 @@ class SjDecoderW(C.Structure):
 
 
 class SjIoSpec(C.Structure):
-    _fields_ = [("ogm_type", C.c_int), ("map_type", C.c_int), ("out_mode", C.c_int)]
+    _fields_ = [("ogm_type", C.c_int), ("map_type", C.c_int), ("out_mode", C.c_int), ("ogm_planes", C.c_int)]
 
 
 class SjEvalParams(C.Structure):

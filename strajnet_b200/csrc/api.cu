@@ -221,7 +221,7 @@ void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBa
 // ---- SwinTransformerEncoder.forward_features (modules.py:570-624) -------------------------------
 void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flow, void* flow_res, void* res0,
                   void* res1, void* res2, const SjEncoderW& w, int B, int S, int large, int ogm_type = IN_F32,
-                  int map_type = IN_F32) {
+                  int map_type = IN_F32, int ogm_es = 2) {  // ogm_es: element stride of the vehicle plane (2: [..,11,2])
   if (w.num_layers != 3 || w.window_size != 8 || w.embed_dim != 96) { c.fail(SJ_EUNSUPPORTED); return; }
   if ((large && S != 512) || (!large && S != 256)) { c.fail(SJ_EUNSUPPORTED); return; }  // Q13
   const int E = w.embed_dim, P = S / 4;
@@ -283,7 +283,7 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
       pe_combine(c, cf, nullptr, B, P, 0, w.pe_flow.norm, none, w.flow_norm, f0, pe_mean, pe_rstd);
       void* cv = c.alloc_act(ntok * E);
       void* cm = c.alloc_act((size_t)B * 4096 * E);
-      embed_tc(ogm, ogm_type, S, 11, 2, w.pe_vec, cv);
+      embed_tc(ogm, ogm_type, S, 11, ogm_es, w.pe_vec, cv);
       embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
       pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, xm, pm_mean, pm_rstd);
     }
@@ -331,12 +331,12 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   if (pe_tc) {
     void* cv = c.alloc_act(B * L0 * E);
     void* cm = c.alloc_act((size_t)B * 4096 * E);
-    embed_tc(ogm, ogm_type, S, 11, 2, w.pe_vec, cv);
+    embed_tc(ogm, ogm_type, S, 11, ogm_es, w.pe_vec, cv);
     embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
     pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, x0, pe_mean, pe_rstd);
   } else {  // patch_embed_vecicle(ogm[...,0]) + patch_embed_map(map) -> all_patch_norm (modules.py:572, :580-587, :602)
     PatchEmbedP p;
-    p.img[0] = ogm; p.itype[0] = ogm_type; p.Cin[0] = 11; p.es[0] = 2; p.S[0] = S;
+    p.img[0] = ogm; p.itype[0] = ogm_type; p.Cin[0] = 11; p.es[0] = ogm_es; p.S[0] = S;
     p.w[0] = w.pe_vec.proj.w; p.bias[0] = w.pe_vec.proj.b; p.g[0] = w.pe_vec.norm.g; p.b[0] = w.pe_vec.norm.b;
     p.img[1] = map_img; p.itype[1] = map_type; p.Cin[1] = 3; p.es[1] = 1; p.S[1] = 256;
     p.w[1] = w.pe_map.proj.w; p.bias[1] = w.pe_map.proj.b; p.g[1] = w.pe_map.norm.g; p.b[1] = w.pe_map.norm.b;
@@ -667,7 +667,8 @@ void strajnet_impl(Ctx& c, const void* ogm, const void* map_img, const float* fl
   }
   {
     RoleScope r(c, "enc");
-    encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm, io.ogm_type, io.map_type);
+    encoder_impl(c, ogm, map_img, flow, flow_res, res0, res1, res2, w.encoder, B, S, w.large_ogm, io.ogm_type, io.map_type,
+                 io.ogm_planes == 1 ? 1 : 2);
   }
   const void* q2 = res2;
   float* off = nullptr;
@@ -742,7 +743,7 @@ using namespace sj;
 
 extern "C" {
 
-int sj_version(void) { return 100; }
+int sj_version(void) { return 101; }
 
 size_t sj_sizeof(int which) {
   switch (which) {
@@ -1075,7 +1076,7 @@ size_t sj_strajnet_workspace_bytes(int B, int S, int dtype) {
   memset(&m, 0, sizeof(m));
   fake_encoder(m.encoder, zb);
   m.fg_msa = 1; m.fg = 1; m.large_ogm = (S == 512);
-  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0};
+  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0, 2};
   return measure(dtype, [&](Ctx& c) { strajnet_impl(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m, B, S, io); });
 }
 int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, const float* obs, const float* occ,
@@ -1083,7 +1084,8 @@ int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, 
                        size_t workspace_bytes, sj_stream_t stream) {
   SJ_REQUIRE(ogm && map_img && flow && obs && occ && out && w && io && B > 0);
   SJ_REQUIRE((io->ogm_type == SJ_IN_F32 || io->ogm_type == SJ_IN_U8) &&
-             (io->map_type == SJ_IN_F32 || io->map_type == SJ_IN_I8_DIV256) && (io->out_mode == 0 || io->out_mode == 1));
+             (io->map_type == SJ_IN_F32 || io->map_type == SJ_IN_I8_DIV256) && (io->out_mode == 0 || io->out_mode == 1) &&
+             (io->ogm_planes == 1 || io->ogm_planes == 2));
   return run(workspace, workspace_bytes, dtype, stream,
              [&](Ctx& c) { strajnet_impl(c, ogm, map_img, flow, obs, occ, out, *w, B, S, *io); });
 }
@@ -1091,7 +1093,7 @@ int sj_strajnet_fwd_io(const void* ogm, const void* map_img, const float* flow, 
 int sj_strajnet_fwd(const float* ogm, const float* map_img, const float* flow, const float* obs, const float* occ,
                     float* out, const SjModelW* w, int B, int S, int dtype, void* workspace, size_t workspace_bytes,
                     sj_stream_t stream) {
-  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0};
+  SjIoSpec io = {SJ_IN_F32, SJ_IN_F32, 0, 2};
   return sj_strajnet_fwd_io(ogm, map_img, flow, obs, occ, out, w, &io, B, S, dtype, workspace, workspace_bytes, stream);
 }
 

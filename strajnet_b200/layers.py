@@ -645,7 +645,7 @@ class STrajNet(Layer):
             return self._launch(out, ogm, map_img, obs, occ, flow)
         self.packed()
         key = (out.data_ptr(), ogm.data_ptr(), map_img.data_ptr(), obs.data_ptr(), occ.data_ptr(), flow.data_ptr(),
-               ogm.shape[0], out.dtype, ogm.dtype, map_img.dtype)
+               ogm.shape[0], out.dtype, ogm.dtype, map_img.dtype, ogm.dim())
         g = self._graphs.get(key)
         if g is not None:
             g.replay()
@@ -677,6 +677,7 @@ class STrajNet(Layer):
         io.ogm_type = L.SJ_IN_U8 if ogm.dtype in (torch.uint8, torch.bool) else L.SJ_IN_F32
         io.map_type = L.SJ_IN_I8_DIV256 if map_img.dtype == torch.int8 else L.SJ_IN_F32
         io.out_mode = 1 if out.dtype == torch.uint8 else 0
+        io.ogm_planes = 1 if ogm.dim() == 4 else 2  # [B,S,S,11]: the vehicle plane alone (the model reads nothing else)
         ws_before = None if self._ws is None else self._ws.data_ptr()
         ws, n = self._workspace(self.workspace_bytes(B))
         if ws_before is not None and ws != ws_before:
@@ -690,8 +691,11 @@ class STrajNet(Layer):
         super().set_weights(weights)
         self._graphs.clear()  # captured graphs point at the old packed weights
 
-    def _raw(self, x, shape, raw_dtypes):
+    def _raw(self, x, shape, raw_dtypes, alt_shape=None):
+        """alt_shape: a second accepted shape (the occupancy raster's vehicle plane alone, [S,S,11])."""
         t = torch.as_tensor(x)
+        if alt_shape is not None and tuple(t.shape[1:]) == tuple(alt_shape):
+            shape = alt_shape
         if t.dtype in raw_dtypes:
             t = t.to(device=self.device).contiguous()
             if tuple(t.shape[1:]) != tuple(shape):
@@ -703,7 +707,7 @@ class STrajNet(Layer):
         """Forward + the reference's submission quantisation (inference.py:124-136,160-182) in one pass:
         uint8 [B,256,256,32]; channel k*4+{0,1}: round(sigmoid*255) (uint8), k*4+{2,3}: clip(round(flow)) (int8 bits)."""
         S = self.cfg["input_size"][0]
-        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool))
+        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool), alt_shape=(S, S, 11))
         map_img = self._raw(map_img, (256, 256, 3), (torch.int8,))
         out = torch.empty(ogm.shape[0], 256, 256, 32, dtype=torch.uint8, device=self.device)
         return self.forward_into(out, ogm, map_img, self._f32(obs, (48, 11, 8)), self._f32(occ, (16, 11, 8)),
@@ -714,7 +718,7 @@ class STrajNet(Layer):
         if obs is None or occ is None or flow is None:
             raise ValueError("STrajNet: obs, occ and flow are required")
         S = self.cfg["input_size"][0]
-        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool))  # bool/uint8 rasters are consumed as they are
+        ogm = self._raw(ogm, (S, S, 11, 2), (torch.uint8, torch.bool), alt_shape=(S, S, 11))  # bool/uint8 rasters are consumed as they are
         map_img = self._raw(map_img, (256, 256, 3), (torch.int8,))      # int8 map bytes are decoded as value/256
         flow = self._f32(flow, (S, S, 2))
         obs = self._f32(obs, (48, 11, 8))

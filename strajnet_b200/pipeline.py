@@ -34,17 +34,19 @@ class Handle:
 
 class InferencePipeline:
     def __init__(self, model, batch: int, depth: int = 2, raw_inputs: bool = False, quantized: bool = False,
-                 graph: bool = True, gather: bool = False, group=None):
+                 graph: bool = True, gather: bool = False, group=None, vehicle_plane_only: bool = False):
         """raw_inputs: ogm arrives as uint8/bool and map_img as int8 (the record's own types, inference.py:91-93);
         quantized: results are the uint8 submission bytes (inference.py:160-182) instead of fp32 logits;
         graph: replay one captured CUDA graph per device slot instead of ~90 stream launches per step;
+        vehicle_plane_only: `ogm` arrives as [B,S,S,11], the one plane of the record's [B,S,S,11,2] raster the model reads
+        (modules.py:572): half the host->device bytes of the largest input;
         gather (data-parallel serving, one process per GPU): every step's result grids are all-gathered on every rank
         (`gathered(slot)`), by `parallel.make_gatherer` on its own stream -- copy engines over NVLink peer memory when
         available, so no SM and no host thread is taken from the forwards; collective: construct on every rank."""
         self.model, self.B, self.depth, self.graph = model, batch, depth, graph
         dev = model.device
         S = model.cfg["input_size"][0]
-        shapes = {"ogm": (batch, S, S, 11, 2), "map_img": (batch, 256, 256, 3), "obs": (batch, 48, 11, 8),
+        shapes = {"ogm": (batch, S, S, 11) if vehicle_plane_only else (batch, S, S, 11, 2), "map_img": (batch, 256, 256, 3), "obs": (batch, 48, 11, 8),
                   "occ": (batch, 16, 11, 8), "flow": (batch, S, S, 2)}
         dts = {k: torch.float32 for k in _KEYS}
         if raw_inputs:

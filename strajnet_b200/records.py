@@ -196,11 +196,13 @@ SCHEMA = {
 }
 
 
-def decode_example(payload, raw: bool = True) -> Dict[str, object]:
+def decode_example(payload, raw: bool = True, vehicle_plane_only: bool = False) -> Dict[str, object]:
     """`_parse_image_function_test` (inference.py:84-96).
 
     raw=True keeps the raster dtypes of the record (ogm uint8 in {0,1}, map_image int8 -- the model divides by 256 on
-    the device); raw=False reproduces the reference's float32 tensors exactly (ogm 0/1, map_image int8/256)."""
+    the device); raw=False reproduces the reference's float32 tensors exactly (ogm 0/1, map_image int8/256).
+    vehicle_plane_only=True returns `ogm[..., 0]` ([S,S,11]), the only plane the model reads (modules.py:572): half the
+    bytes of the largest input on its way to the GPU (STrajNet and InferencePipeline accept either shape)."""
     d = parse_example(payload)
     out: Dict[str, object] = {}
     for name, (dt, shape) in SCHEMA.items():
@@ -214,6 +216,8 @@ def decode_example(payload, raw: bool = True) -> Dict[str, object]:
         if name in ("centerlines", "actors", "occl_actors"):
             a = a.astype(np.float32)  # tf.cast(float64 -> float32)
         elif name == "ogm":
+            if vehicle_plane_only:
+                a = a[..., 0]
             a = (a != 0).astype(np.uint8) if raw else (a != 0).astype(np.float32)
         elif name == "map_image" and not raw:
             a = a.astype(np.float32) / 256

@@ -509,3 +509,16 @@ def test_inference_pipeline_stale_handle_raises(sj):
         h0.result()
     assert torch.equal(h1.result(), h2.result())
     pipe.synchronize()
+
+
+def test_vehicle_plane_only_input_is_bit_identical(sj):
+    """ogm handed over as its vehicle plane alone ([B,S,S,11], uint8 or fp32) gives the same bits as the record's
+    [B,S,S,11,2] raster, of which the model reads plane 0 only (modules.py:572)."""
+    for dtype in ("float32", "bfloat16"):
+        m = _model(sj, dtype=dtype)
+        inp = O.make_inputs(2, 256, seed=41)
+        y = _fwd(m, inp)
+        plane = inp["ogm"][..., 0].contiguous()
+        y1 = m(plane, inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
+        y2 = m((plane != 0).to(torch.uint8), inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
+        assert torch.equal(y, y1) and torch.equal(y, y2)

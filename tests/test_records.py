@@ -109,6 +109,8 @@ def test_decode_example_matches_reference_decode(tmp_path):
     b = R.batch_examples([raw, raw])
     assert b["ogm"].shape == (2, 512, 512, 11, 2) and b["obs"].shape == (2, 48, 11, 8) and b["map_img"].shape == (2, 256, 256, 3)
     assert b["occ"].shape == (2, 16, 11, 8) and b["mapt"].shape == (2, 256, 10, 7) and b["flow"].shape == (2, 512, 512, 2)
+    veh = R.decode_example(rec, raw=True, vehicle_plane_only=True)  # the one plane the model reads (modules.py:572)
+    assert veh["ogm"].shape == (512, 512, 11) and np.array_equal(veh["ogm"], raw["ogm"][..., 0])
 
 
 def test_decode_example_rejects_wrong_sizes():
