@@ -332,9 +332,10 @@ def main():
     host_raw["ogm"] = (host["ogm"][..., 0] != 0).to(torch.uint8).contiguous().pin_memory()
     host_raw["map_img"] = torch.round(host["map_img"] * 256).to(torch.int8).pin_memory()
     depth = int(os.environ.get("SJ_E2E_DEPTH", "2"))
-    pipes = {"raw": (InferencePipeline(model, B, depth=depth, raw_inputs=True, quantized=True, gather=world > 1,
+    e2e_gather = world > 1 and os.environ.get("SJ_E2E_NO_GATHER") is None  # diagnosis knob: e2e without the all-gather
+    pipes = {"raw": (InferencePipeline(model, B, depth=depth, raw_inputs=True, quantized=True, gather=e2e_gather,
                                        vehicle_plane_only=True), host_raw),
-             "fp32": (InferencePipeline(model, B, depth=depth, gather=world > 1), host)}
+             "fp32": (InferencePipeline(model, B, depth=depth, gather=e2e_gather), host)}
     pipe, host_e2e = pipes["raw"]
     pending = []
 
@@ -438,7 +439,7 @@ def main():
 
     ms_e2e = time_e2e()
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    e2e_gather = pipe.gather_kind
+    e2e_gather_kind = pipe.gather_kind
     pipe, host_e2e = pipes["fp32"]
     for _ in range(3):
         step_e2e()
@@ -504,7 +505,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps,
                     "how": "InferencePipeline(raw_inputs, quantized, vehicle_plane_only): pinned host -> device (uint8 vehicle-plane raster [B,S,S,11], int8 map, fp32 flow/actors), forward, fused submission quantisation, device -> pinned host (uint8 grids) every "
                            "step; 3 streams, double-buffered; synchronised wall clock, max over ranks"
-                           + (f"; every step's uint8 grids all-gathered on every rank ({e2e_gather})" if world > 1 else ""),
+                           + (f"; every step's uint8 grids all-gathered on every rank ({e2e_gather_kind})" if e2e_gather else ""),
                     "fp32_io": {"value": world * B * args.steps / (ms_e2e_fp32 / 1e3), "unit": UNIT,
                                 "h2d_bytes_per_step": h2d_fp32, "d2h_bytes_per_step": d2h_fp32}},
             "gpu_launches": int(launches_per_step * args.steps),
