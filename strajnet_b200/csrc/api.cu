@@ -505,9 +505,12 @@ void traj_cross_impl(Ctx& c, const void* pic, const void* key, const int* cmask,
     GemmP g;
     g.A = Oc; g.lda = 128; g.set_weights(w.ca_proj); g.ldw = 128; g.w_gstride = 128 * 128;
     g.bias_gstride = 128; g.C = P1; g.ldc = 128; g.M = MQ; g.N = 128; g.K = 128; g.groups = 8; g.am = pm; g.cm = pm;
+    // norm1 statistics (eps 1e-3) of the projected rows straight from this epilogue on the tensor-core path
+    const bool st = c.dtype == SJ_BF16 && w.ca_proj.w_tc && tc_gemm_stats_ok(128);
+    if (st) { g.st_mean = mean; g.st_rstd = rstd; g.st_eps = 1e-3f; }
     gemm(c, g);
+    if (!st) ln_stats(c, P1, B * 2048, 128, 128, 1e-3f, mean, rstd);
   }
-  ln_stats(c, P1, B * 2048, 128, 128, 1e-3f, mean, rstd);
   {
     GemmP g;
     g.A = P1; g.lda = 128; g.set_weights(w.ca_ffn1); g.ldw = 512; g.w_gstride = 128 * 512;
