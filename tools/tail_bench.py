@@ -1,5 +1,5 @@
 """Times the decoder tail (2 x tc_upconv4h + head_tapsum) at batch 16 with CUDA events, per role.
-usage: python tools/tail_bench.py [B]    (ablations: SJ_UP4H_DBG=<bits> in the environment)"""
+usage: python tools/tail_bench.py [B]"""
 import ctypes as C
 import os
 import sys
@@ -47,5 +47,5 @@ for _ in range(10):
     run()
 e1.record()
 torch.cuda.synchronize()
-print(f"dbg={os.environ.get('SJ_UP4H_DBG', '0'):>3} B={B} tail {e0.elapsed_time(e1) / 10:.4f} ms | " +
+print(f"B={B} tail {e0.elapsed_time(e1) / 10:.4f} ms | " +
       " | ".join(f"{k} {v * 1e3:.1f} us" for k, v in res.items()))
