@@ -235,6 +235,17 @@ int sj_patch_merging_fwd(const void* x, void* y, const SjPatchMergeW* w, const v
 int sj_patch_embed_fwd(const float* img, void* y, const SjPatchEmbedW* w, int B, int S, int Cin, int elem_stride,
                        int E, int dtype, sj_stream_t stream);
 
+/* The encoder's embedding stage as one tcgen05 kernel (bf16 only; modules.py:572-587 + :602, and :576-577 for the flow
+ * branch):  y = LN_final( PatchEmbed_0(img0) [+ PatchEmbed_1(img1)] ), bf16 [B,(S0/4)^2,96].
+ * img0 [B,S0,S0,Cin0] of input type type0 (SjInputType below: 0 fp32, 1 bool bytes, 2 int8/256) with element stride es0
+ * (2 selects plane 0 of ogm[...,11,2]); img1 [B,S1,S1,Cin1] or NULL: its S1/4 x S1/4 tokens are added at token offset
+ * (pad1, pad1) of the grid (32 in 512-input mode, modules.py:582-585), tokens outside get no term.
+ * st_mean / st_rstd: fp32 [B*(S0/4)^2] LayerNorm (eps 1e-5) statistics of y, or NULL.  Needs w*->proj.w_tc and 16*Cin0 <= 192,
+ * 16*Cin1 <= 64, S0/4 in {64,128}; otherwise SJ_EUNSUPPORTED. */
+int sj_patch_embed_sum_fwd(const void* img0, int type0, int S0, int Cin0, int es0, const SjPatchEmbedW* w0, const void* img1,
+                           int type1, int S1, int Cin1, const SjPatchEmbedW* w1, int pad1, const SjNorm* final_norm, int B,
+                           void* y, float* st_mean, float* st_rstd, sj_stream_t stream);
+
 /* BasicLayer.call, modules.py:351-364: returns (x_down or x, res).  y_down may be NULL when !has_down. */
 size_t sj_basic_layer_workspace_bytes(int B, int H, int W, int C, int dtype);
 int sj_basic_layer_fwd(const void* x, void* y_down, void* res, const SjBasicLayerW* w, int B, int H, int W,

@@ -126,6 +126,8 @@ SIGNATURES = {
     "sj_decoder_fwd": (_i, [_p, _p, _p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p, _sz, _p]),
     "sj_upconv_fwd": (_i, [_p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
     "sj_res_add_fwd": (_i, [_p, _p, _p, C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
+    "sj_patch_embed_sum_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(SjPatchEmbedW), _p, _i, _i, _i, C.POINTER(SjPatchEmbedW), _i,
+                                    C.POINTER(SjNorm), _i, _p, _p, _p, _p]),
     "sj_res_add2_fwd": (_i, [_p, _p, _p, _p, _p, C.POINTER(SjLinear), C.POINTER(SjLinear), _i, _i, _i, _i, _i, _p]),
     "sj_out_head_fwd": (_i, [_p, _p, _p, C.POINTER(SjDecoderW), _i, _i, _i, _p]),
     "sj_decoder_tail_workspace_bytes": (_sz, [_i, _i]),

@@ -243,6 +243,10 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   bool pe_stats = false;
   // bf16 mode: the 4x4/s4 patch convs run as tcgen05 GEMMs over an im2col'ed bf16 matrix
   const bool pe_tc = c.dtype == SJ_BF16 && w.pe_vec.proj.w_tc && w.pe_map.proj.w_tc && w.pe_flow.proj.w_tc;
+  // ... or, by default, inside ONE kernel per branch that builds the im2col tile in shared memory and finishes the tokens
+  // (tc_patch_embed.cu); SJ_DISABLE_FUSED_PE=1 keeps the im2col -> GEMM -> combine chain
+  static const bool pe_fused_off = getenv("SJ_DISABLE_FUSED_PE") != nullptr;
+  const bool pe_fused = pe_tc && !pe_fused_off && tc_patch_embed_supported(B, P, 11, 3, 64, large ? 32 : 0);
   auto embed_tc = [&](const void* img, int itype, int Simg, int Cin, int es, const SjPatchEmbedW& pw, void* conv_out) {
     const int Kpad = (16 * Cin + 63) / 64 * 64;
     const int Mtok = B * (Simg / 4) * (Simg / 4);
@@ -277,6 +281,12 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     float* pm_mean = (float*)c.alloc(ntok * 4);
     float* pm_rstd = (float*)c.alloc(ntok * 4);
     {
+    RoleScope rpe(c, "enc.pe");
+    if (pe_fused) {
+      tc_patch_embed(c, flow, IN_F32, S, 2, 1, w.pe_flow, nullptr, 0, 0, 0, nullptr, 0, w.flow_norm, B, f0, pe_mean, pe_rstd);
+      tc_patch_embed(c, ogm, ogm_type, S, 11, ogm_es, w.pe_vec, map_img, map_type, 256, 3, &w.pe_map, large ? 32 : 0,
+                     w.all_patch_norm, B, xm, pm_mean, pm_rstd);
+    } else {
       void* cf = c.alloc_act(ntok * E);
       embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
       SjNorm none{};
@@ -286,6 +296,7 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
       embed_tc(ogm, ogm_type, S, 11, ogm_es, w.pe_vec, cv);
       embed_tc(map_img, map_type, 256, 3, 1, w.pe_map, cm);
       pe_combine(c, cv, cm, B, P, large ? 32 : 0, w.pe_vec.norm, w.pe_map.norm, w.all_patch_norm, xm, pm_mean, pm_rstd);
+    }
     }
     void* t1[2] = {c.alloc_act(ntok * E), c.alloc_act(ntok * E)};    // x + attention
     void* mid[2] = {c.alloc_act(ntok * E), c.alloc_act(ntok * E)};   // output of block 0
@@ -312,7 +323,10 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
     patch_merging_impl(c, full[0], flow_x, lf.down, nullptr, B, P, P, 96);
     patch_merging_impl(c, full[1], x1, l0.down, flow_x, B, P, P, 96);  // + flow_x (modules.py:613)
   } else {
-  if (pe_tc) {
+  if (pe_fused) {
+    tc_patch_embed(c, flow, IN_F32, S, 2, 1, w.pe_flow, nullptr, 0, 0, 0, nullptr, 0, w.flow_norm, B, f0, pe_mean, pe_rstd);
+    pe_stats = true;
+  } else if (pe_tc) {
     void* cf = c.alloc_act(B * L0 * E);
     embed_tc(flow, IN_F32, S, 2, 1, w.pe_flow, cf);
     SjNorm none{};
@@ -328,7 +342,10 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   basic_layer_impl(c, f0, flow_x, full[0], w.flow_layer, nullptr, B, P, P, 8, pe_stats ? pe_mean : nullptr,
                    pe_stats ? pe_rstd : nullptr);
   void* x0 = f0;  // f0 is dead once the flow layer has run
-  if (pe_tc) {
+  if (pe_fused) {
+    tc_patch_embed(c, ogm, ogm_type, S, 11, ogm_es, w.pe_vec, map_img, map_type, 256, 3, &w.pe_map, large ? 32 : 0,
+                   w.all_patch_norm, B, x0, pe_mean, pe_rstd);
+  } else if (pe_tc) {
     void* cv = c.alloc_act(B * L0 * E);
     void* cm = c.alloc_act((size_t)B * 4096 * E);
     embed_tc(ogm, ogm_type, S, 11, ogm_es, w.pe_vec, cv);
@@ -947,6 +964,15 @@ int sj_patch_embed_fwd(const float* img, void* y, const SjPatchEmbedW* w, int B,
     p.w[0] = w->proj.w; p.bias[0] = w->proj.b; p.g[0] = w->norm.g; p.b[0] = w->norm.b;
     p.n_in = 1; p.y = y; p.B = B; p.E = E;
     patch_embed(c, p);
+  });
+}
+
+int sj_patch_embed_sum_fwd(const void* img0, int type0, int S0, int Cin0, int es0, const SjPatchEmbedW* w0, const void* img1,
+                           int type1, int S1, int Cin1, const SjPatchEmbedW* w1, int pad1, const SjNorm* final_norm, int B,
+                           void* y, float* st_mean, float* st_rstd, sj_stream_t stream) {
+  SJ_REQUIRE(img0 && w0 && final_norm && y && B > 0 && S0 > 0 && (!img1 || (w1 && S1 > 0)) && (!st_mean == !st_rstd));
+  return run(nullptr, 0, SJ_BF16, stream, [&](Ctx& c) {
+    tc_patch_embed(c, img0, type0, S0, Cin0, es0, *w0, img1, type1, S1, Cin1, w1, pad1, *final_norm, B, y, st_mean, st_rstd);
   });
 }
 

@@ -243,6 +243,13 @@ bool tc_resadd2_supported(int HW, int Cin, int Cout);
 void tc_resadd2(Ctx& c, const void* skip_a, const void* skip_b, const void* src, void* dst_a, void* dst_b, const void* wa_tc,
                 const float* bias_a, const void* wb_tc, const float* bias_b, int B, int HW);
 
+// fused patch embedding (tc_patch_embed.cu): img0 [B,S0,S0,Cin0(,es0)] (+ img1 [B,S1,S1,Cin1] covering tokens
+// [pad1, pad1 + S1/4) of the grid) -> y bf16 [B,(S0/4)^2,96] = LN_f(LN_0(conv_0) [+ LN_1(conv_1)]) + norm1 statistics
+bool tc_patch_embed_supported(int B, int P, int Cin0, int Cin1, int P1, int pad1);
+void tc_patch_embed(Ctx& c, const void* img0, int itype0, int S0, int Cin0, int es0, const SjPatchEmbedW& pw0,
+                    const void* img1, int itype1, int S1, int Cin1, const SjPatchEmbedW* pw1, int pad1, const SjNorm& nf,
+                    int B, void* y, float* st_mean, float* st_rstd);
+
 // ---- validation-side loss / metrics (eval.cu) ----------------------------------------------------
 size_t eval_workspace_bytes();
 void eval_forward(Ctx& c, const float* pred, const float* gt_obs, const float* gt_occ, const float* gt_flow,

@@ -366,3 +366,83 @@ def test_res_add2_fused_tight(env, B, inplace):
     yb = dst_b.float().cpu()
     ex = (yb - ref_b).abs() - (REL * ref_b.abs() + ABS)
     assert ex.max().item() <= 0, f"res_add2 fx: exceeds one output rounding by {ex.max().item():.3e}"
+
+
+def _pe_weights(cin, seed):
+    return {"proj.kernel": randn((4, 4, cin, 96), seed, (1.0 / (16 * cin)) ** 0.5), "proj.bias": randn((96,), seed + 1, 0.1),
+            "norm.gamma": 1 + randn((96,), seed + 2, 0.1), "norm.beta": randn((96,), seed + 3, 0.1)}
+
+
+def _pe_conv(x, w):
+    """4x4 / stride 4 conv of bf16-rounded pixels with the bf16-rounded kernel (the tensor-core operands), fp32 LN."""
+    y = O.conv2d_nhwc(_bf(x), _bf(w["proj.kernel"]), w["proj.bias"], stride=4)
+    B, Hp, Wp, E = y.shape
+    return O.layer_norm(y.reshape(B, Hp * Wp, E), w["norm.gamma"], w["norm.beta"], 1e-5).reshape(B, Hp, Wp, E)
+
+
+@pytest.mark.parametrize("case", ["flow", "raster_f32", "raster_raw", "raster_plane", "raster_512"])
+def test_patch_embed_fused_tight(env, case):
+    """tc_patch_embed: im2col in shared memory + tcgen05 projections + the LayerNorms and the sum in the epilogue, against
+    fp32 torch on the same bf16 operands with one output rounding (modules.py:572-587, :602; :576-577 for `flow`).
+    raster_raw feeds the record's own bool / int8 bytes, raster_plane the [.., 11] vehicle plane alone, raster_512 the
+    512-input mode where the map only covers the centre 64 x 64 tokens."""
+    _lib, weights, dev = env
+    lib = _lib.lib()
+    B = 3
+    S = 512 if case == "raster_512" else 256
+    P = S // 4
+    nf = {"gamma": 1 + randn((96,), 90, 0.1), "beta": randn((96,), 91, 0.1)}
+    pk_n = weights.Packer({"n.gamma": nf["gamma"], "n.beta": nf["beta"]}, dev, tc=True)
+    norm_f = pk_n.norm("n.")
+    if case == "flow":
+        w0 = _pe_weights(2, 80)
+        img0 = randn((B, S, S, 2), 81)
+        x0, t0, es0, cin0 = img0, _lib.SJ_IN_F32, 1, 2
+        d0 = img0.to(dev)
+        w1 = img1 = d1 = None
+    else:
+        w0, w1 = _pe_weights(11, 82), _pe_weights(3, 86)
+        if case == "raster_raw":
+            ogm = (randn((B, S, S, 11, 2), 83) > 0.5)
+            d0, t0, es0 = ogm.view(torch.uint8).to(dev), _lib.SJ_IN_U8, 2
+            x0 = ogm[..., 0].float()
+            m8 = (randn((B, 256, 256, 3), 84) * 60).clamp(-128, 127).to(torch.int8)
+            d1, t1, img1 = m8.to(dev), _lib.SJ_IN_I8_DIV256, m8.float() / 256.0
+        else:
+            ogm = randn((B, S, S, 11, 2), 83)
+            if case == "raster_plane":
+                d0, es0 = ogm[..., 0].contiguous().to(dev), 1
+            else:
+                d0, es0 = ogm.to(dev), 2
+            t0, x0 = _lib.SJ_IN_F32, ogm[..., 0]
+            img1 = randn((B, 256, 256, 3), 84)
+            d1, t1 = img1.to(dev), _lib.SJ_IN_F32
+        cin0 = 11
+    pk0 = weights.Packer(w0, dev, tc=True)
+    pe0 = pk0.patch_embed("")
+    pe1 = None
+    if w1 is not None:
+        pk1 = weights.Packer(w1, dev, tc=True)
+        pe1 = pk1.patch_embed("")
+    y = torch.empty(B, P * P, 96, dtype=torch.bfloat16, device=dev)
+    mean = torch.empty(B * P * P, dtype=torch.float32, device=dev)
+    rstd = torch.empty_like(mean)
+    pad1 = (P - 64) // 2
+    lib.sj_tc_launch_count(1)
+    _lib.check(lib.sj_patch_embed_sum_fwd(d0.data_ptr(), t0, S, cin0, es0, C.byref(pe0),
+                                          d1.data_ptr() if d1 is not None else None, t1 if d1 is not None else 0, 256, 3,
+                                          C.byref(pe1) if pe1 is not None else None, pad1, C.byref(norm_f), B, y.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), _stream()), "patch_embed_sum")
+    torch.cuda.synchronize()
+    assert lib.sj_tc_launch_count(1) == 1, "the fused patch-embedding kernel did not run"
+    t = _pe_conv(x0, w0)
+    if w1 is not None:
+        m = _pe_conv(img1, w1)
+        t = t.clone()
+        t[:, pad1:pad1 + 64, pad1:pad1 + 64] += m
+    ref = O.layer_norm(t, nf["gamma"], nf["beta"], 1e-5)
+    yc = y.float().cpu().reshape(B, P, P, 96)
+    _assert_tight(yc, ref, f"patch_embed {case}", abs_=2e-3)
+    mu, rs = _ln_stats(yc.reshape(-1, 96))
+    assert (mean.cpu() - mu.reshape(-1)).abs().max().item() < 1e-4
+    assert ((rstd.cpu() - rs.reshape(-1)).abs() / rs.reshape(-1)).max().item() < 1e-3
