@@ -48,7 +48,7 @@ struct PeIn {
   int itype, S, Cin, es, P, pad, nkc;  // P = S / 4 tokens per row; pad: this input covers tokens [pad, pad + P) of the grid
   int run, span_u;                     // source elements per (token, kernel row); 16-byte units per (token row, kernel row)
   long long row_bytes;                 // bytes of one image row
-  uint32_t m_span, m_run;              // magic multipliers: u / span_u, and e / (run / 4) (fp32) or e / run (bytes)
+  uint32_t m_run;                      // magic multiplier: e / (run / 4) (fp32) or e / run (bytes)
   const float* bias;
   const float* g;
   const float* b;
@@ -74,59 +74,66 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// four consecutive source elements x[0..3] of one token, starting at source offset j (a multiple of 4) of kernel row ky:
-// element stride 1 keeps all four (K indices kb + j .. + 3), element stride 2 keeps x0 and x2 (K indices kb + j/2, + 1)
-template <int ES>
-__device__ __forceinline__ void put4(uint8_t* tile, int r, int kb, int j, float x0, float x1, float x2, float x3) {
-  if (ES == 2)
-    *reinterpret_cast<uint32_t*>(a_addr(tile, r, kb + (j >> 1))) = bf2(x0, x2);
-  else
-    *reinterpret_cast<uint2*>(a_addr(tile, r, kb + j)) = make_uint2(bf2(x0, x1), bf2(x2, x3));
-}
 template <int ITYPE>
 __device__ __forceinline__ float cvt_byte(uint32_t byte) {
   return ITYPE == IN_U8 ? (byte != 0 ? 1.0f : 0.0f) : (float)(int8_t)byte / 256.0f;
 }
 
-// One input's share of a tile.  The source is nseg = 4 x token rows contiguous segments (one per token row and kernel
-// row, `row_bytes` apart); their 16-byte units are dealt round-robin to the threads, and each thread keeps LB loads in
-// flight before it converts and scatters them: the loads are latency-bound, so this is ~3 round trips to HBM per tile
-// instead of two per segment.
+// One input's share of a tile.  The source is nseg = 4 x token rows contiguous segments (segment = 4 * token row + kernel
+// row, `row_bytes` apart) of span_u 16-byte units each.  A thread owns unit positions e = tid, tid + 256, ...: where a
+// position lands in the tile (token, offset inside the token's run) is the same in every segment, so it is worked out
+// once and the thread then loads that position of ALL segments (up to 8 loads in flight) before it converts and scatters
+// them; segment-dependent terms (row block, kernel row) are compile-time in the unrolled loops.
 template <int ITYPE, int ES>
-__device__ __forceinline__ void load_tile(uint8_t* tileA, const uint8_t* img_b, long long row_bytes, int total, int span_u,
-                                       uint32_t m_span, uint32_t m_run, int run, int Cin, int pad, int P, int tid) {
-  constexpr int LB = ITYPE == IN_F32 ? 8 : 4;
-  for (int u0 = tid; u0 < total; u0 += NTHREADS * LB) {
-    uint4 v[LB];
+__device__ __forceinline__ void load_tile(uint8_t* tileA, const uint8_t* img_b, long long row_bytes, int nseg, int span_u,
+                                          uint32_t m_run, int run, int Cin, int pad, int P, int tid) {
+  constexpr int G = ITYPE == IN_F32 ? 1 : 4;  // 4-element groups per 16-byte unit
+  for (int e = tid; e < span_u; e += NTHREADS) {
+    int rowoff[G], kq[G];  // byte offset of the token's tile row within its token row block; K offset within the kernel row
+    {
+      int tk, j;
+      if (ITYPE == IN_F32) {
+        tk = __umulhi(e, m_run);  // m_run divides by run / 4 here
+        j = (e - tk * (run >> 2)) << 2;
+      } else {
+        tk = __umulhi(e << 4, m_run);
+        j = (e << 4) - tk * run;
+      }
 #pragma unroll
-    for (int l = 0; l < LB; ++l) {
-      const int u = u0 + l * NTHREADS;
-      if (u < total) {
-        const int seg = __umulhi(u, m_span), e = u - seg * span_u;  // seg = 4 * token row + kernel row
-        v[l] = __ldg(reinterpret_cast<const uint4*>(img_b + seg * row_bytes) + e);
+      for (int g = 0; g < G; ++g) {
+        rowoff[g] = (pad + tk) * 128;
+        kq[g] = ES == 2 ? j >> 1 : j;
+        j += 4;
+        if (j >= run) { j = 0; ++tk; }
       }
     }
+    const uint8_t* src = img_b + (long long)e * 16;
+    uint4 v[8];
 #pragma unroll
-    for (int l = 0; l < LB; ++l) {
-      const int u = u0 + l * NTHREADS;
-      if (u < total) {
-        const int seg = __umulhi(u, m_span), e = u - seg * span_u;
-        const int r0 = (seg >> 2) * P + pad, kb = (seg & 3) * 4 * Cin;
-        if (ITYPE == IN_F32) {
-          const int tk = __umulhi(e, m_run);  // m_run divides by run / 4 here
-          put4<ES>(tileA, r0 + tk, kb, (e - tk * (run >> 2)) << 2, __uint_as_float(v[l].x), __uint_as_float(v[l].y),
-                   __uint_as_float(v[l].z), __uint_as_float(v[l].w));
-        } else {
-          int tk = __umulhi(e << 4, m_run), j = (e << 4) - tk * run;
-          const uint32_t wv[4] = {v[l].x, v[l].y, v[l].z, v[l].w};
+    for (int sg = 0; sg < 8; ++sg)
+      if (sg < nseg) v[sg] = __ldg(reinterpret_cast<const uint4*>(src + sg * row_bytes));
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w = wv[q];
-            put4<ES>(tileA, r0 + tk, kb, j, cvt_byte<ITYPE>(w & 0xff), cvt_byte<ITYPE>((w >> 8) & 0xff),
-                     cvt_byte<ITYPE>((w >> 16) & 0xff), cvt_byte<ITYPE>(w >> 24));
-            j += 4;
-            if (j >= run) { j = 0; ++tk; }
+    for (int sg = 0; sg < 8; ++sg) {
+      if (sg < nseg) {
+        const int rbase = (sg >> 2) * P * 128, kb = (sg & 3) * 4 * Cin;
+        const uint32_t wv[4] = {v[sg].x, v[sg].y, v[sg].z, v[sg].w};
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int k = kb + kq[g], ro = rbase + rowoff[g];
+          uint8_t* dst = tileA + (k >> 6) * A_CHUNK + ro + ((((k >> 3) ^ (ro >> 7)) & 7) << 4) + (k & 7) * 2;
+          float x0, x1, x2, x3;
+          if (ITYPE == IN_F32) {
+            x0 = __uint_as_float(wv[0]); x1 = __uint_as_float(wv[1]); x2 = __uint_as_float(wv[2]); x3 = __uint_as_float(wv[3]);
+          } else {
+            const uint32_t w = wv[g];
+            x0 = cvt_byte<ITYPE>(w & 0xff); x1 = cvt_byte<ITYPE>((w >> 8) & 0xff);
+            x2 = cvt_byte<ITYPE>((w >> 16) & 0xff); x3 = cvt_byte<ITYPE>(w >> 24);
           }
+          // element stride 1 keeps all four (K indices k .. k + 3), element stride 2 keeps x0 and x2 (K indices k, k + 1)
+          if (ES == 2)
+            *reinterpret_cast<uint32_t*>(dst) = bf2(x0, x2);
+          else
+            *reinterpret_cast<uint2*>(dst) = make_uint2(bf2(x0, x1), bf2(x2, x3));
         }
       }
     }
@@ -261,11 +268,9 @@ tc_patch_embed_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     // ---- im2col in shared memory ----
     // the K padding of A0 (16-byte chunks [2 Cin, 8 nkc) of every row) held staging data: zero it again
     {
-      const int z0 = 2 * p.in[0].Cin, nz = 8 * p.in[0].nkc - z0;
-      for (int u = tid; u < BM * nz; u += NTHREADS) {
-        const int r = u / nz, kc = z0 + (u - r * nz);
-        *reinterpret_cast<uint4*>(a_addr(smem + OFF_A0, r, kc * 8)) = make_uint4(0, 0, 0, 0);
-      }
+      const int z0 = 2 * p.in[0].Cin, z1 = 8 * p.in[0].nkc;
+      if (tid < BM)
+        for (int kc = z0; kc < z1; ++kc) *reinterpret_cast<uint4*>(a_addr(smem + OFF_A0, tid, kc * 8)) = make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {  // unrolled: p.in[] must be indexed statically (kernel parameter space)
@@ -273,12 +278,11 @@ tc_patch_embed_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
       const PeIn& in = p.in[i];
       if (in.pad != 0 && (pi0 - in.pad < 0 || pi0 - in.pad >= in.P)) continue;  // this token row has no input-i tokens
       uint8_t* tileA = smem + (i == 0 ? OFF_A0 : OFF_A1);
-      const int total = rows_per_tile * 4 * in.span_u;
       const uint8_t* img_b = reinterpret_cast<const uint8_t*>(in.img) + ((long long)b * in.S + 4 * (pi0 - in.pad)) * in.row_bytes;
       if (i == 0)
-        load_tile<T0, ES0>(tileA, img_b, in.row_bytes, total, in.span_u, in.m_span, in.m_run, in.run, in.Cin, in.pad, p.P, tid);
+        load_tile<T0, ES0>(tileA, img_b, in.row_bytes, rows_per_tile * 4, in.span_u, in.m_run, in.run, in.Cin, in.pad, p.P, tid);
       else
-        load_tile<(T1 < 0 ? 0 : T1), 1>(tileA, img_b, in.row_bytes, total, in.span_u, in.m_span, in.m_run, in.run, in.Cin, in.pad, p.P, tid);
+        load_tile<(T1 < 0 ? 0 : T1), 1>(tileA, img_b, in.row_bytes, rows_per_tile * 4, in.span_u, in.m_run, in.run, in.Cin, in.pad, p.P, tid);
     }
     fence_async_smem();
     __syncthreads();
@@ -417,7 +421,6 @@ void tc_patch_embed(Ctx& c, const void* img0, int itype0, int S0, int Cin0, int 
     in.span_u = in.P * in.run / upe;
     in.row_bytes = (long long)S * Cin * es * esz;
     auto magic = [](uint32_t d) { return (uint32_t)((1ull << 32) / d + 1); };  // exact for u * d < 2^32, d >= 2
-    in.m_span = magic(in.span_u);
     in.m_run = magic(itype == IN_F32 ? in.run / 4 : in.run);
     in.bias = pw.proj.b; in.g = pw.norm.g; in.b = pw.norm.b;
   };
@@ -436,6 +439,9 @@ void tc_patch_embed(Ctx& c, const void* img0, int itype0, int S0, int Cin0, int 
     c.fail(SJ_ECUDA);
     return;
   }
+  // two persistent CTAs per SM.  (One tile per CTA, 512 CTAs at batch 16, so that later waves stagger the load and epilogue
+  // phases: 83 us for the two launches against 80 us; an L2 prefetch of the next tile's rows during the epilogue: no change,
+  // the loads run at L2 -> SM bandwidth either way.)
   const int grid = p.num_tiles < 2 * num_sms() ? p.num_tiles : 2 * num_sms();
   bool launched = false;
   const int t1 = n_in > 1 ? itype1 : -1;
