@@ -66,6 +66,14 @@ void linear(Ctx& c, const void* A, int lda, const SjLinear& w, void* C, int ldc,
   gemm(c, g);
 }
 
+// does the attention half of this block run as the one fused tcgen05 kernel (tc_wmsa.cu)?
+// SJ_DISABLE_FUSED_WMSA=1: never; SJ_WMSA_MAX_C=96: only the 96-channel stages (A/B of the 192-channel instance)
+bool wmsa_fused_ok(const Ctx& c, const SjSwinBlockW& w, int B, int H, int W, int C, int heads, int ws, int shift) {
+  static const bool off = getenv("SJ_DISABLE_FUSED_WMSA") != nullptr;
+  static const int max_c = getenv("SJ_WMSA_MAX_C") ? atoi(getenv("SJ_WMSA_MAX_C")) : 1 << 30;
+  return c.dtype == SJ_BF16 && !off && C <= max_c && w.qkv_ln.w_tc && tc_wmsa_supported(B, H, W, C, heads, ws, shift);
+}
+
 // ---- SwinTransformerBlock.call (modules.py:220-262) ---------------------------------------------
 // in_mean/in_rstd: norm1 statistics of x when the producer of x already emitted them; out_mean/out_rstd: where to put
 // the eps-1e-5 LayerNorm statistics of y for the next block.  Returns true when the out statistics were written
@@ -96,7 +104,7 @@ bool swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
   static const bool fused_off = getenv("SJ_DISABLE_FUSED_WMSA") != nullptr;
   static const bool stats_off = getenv("SJ_DISABLE_FUSED_STATS") != nullptr;
   const bool tc = c.dtype == SJ_BF16 && w.proj.w_tc && w.fc2.w_tc;
-  const bool fused = c.dtype == SJ_BF16 && !fused_off && w.qkv_ln.w_tc && tc_wmsa_supported(B, H, W, C, heads, ws, shift);
+  const bool fused = !fused_off && wmsa_fused_ok(c, w, B, H, W, C, heads, ws, shift);
   // norm2 / next-block norm1 statistics straight out of the producing epilogue (one n-tile must cover the row)
   const bool stats_fused = tc && !stats_off && tc_gemm_stats_ok(C);
   bool have_stats2 = false;
@@ -106,7 +114,7 @@ bool swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
       ln_stats(c, x, (int)M, C, C, 1e-5f, mean, rstd);
       in_mean = mean; in_rstd = rstd;
     }
-    tc_wmsa(c, x, x1, in_mean, in_rstd, w, B, H, W, shift, mean2, rstd2);
+    tc_wmsa(c, x, x1, in_mean, in_rstd, w, B, H, W, C, shift, mean2, rstd2);
     have_stats2 = true;
   } else if (c.dtype == SJ_BF16) {
     // tensor-core path: norm1 + roll + partition as one gather pass, then a plain GEMM
@@ -193,8 +201,8 @@ void basic_layer_impl(Ctx& c, const void* x, void* y_down, void* res, const SjBa
     for (int j = 0; j < 2; ++j) st[i][j] = (float*)c.alloc((size_t)B * H * W * 4);
   const int sh = (H <= ws || W <= ws) ? 0 : ws / 2;
   // the fused window-MSA kernel derives the partition from TMA coordinates: no token maps needed
-  const bool all_fused = c.dtype == SJ_BF16 && getenv("SJ_DISABLE_FUSED_WMSA") == nullptr && w.blocks_host[0].qkv_ln.w_tc &&
-                         tc_wmsa_supported(B, H, W, C, w.heads, ws, 0) && tc_wmsa_supported(B, H, W, C, w.heads, ws, sh);
+  const bool all_fused = wmsa_fused_ok(c, w.blocks_host[0], B, H, W, C, w.heads, ws, 0) &&
+                         wmsa_fused_ok(c, w.blocks_host[0], B, H, W, C, w.heads, ws, sh);
   if (!all_fused) {
     window_token_map(c, H, W, ws, 0, maps[0]);
     window_token_map(c, H, W, ws, sh, maps[1]);

@@ -205,12 +205,12 @@ void out_conv(Ctx& c, const void* x_occ, const void* x_flow, const float* w, con
 // crop the centre of x [B,P,P,C] -> y [B,P/2,P/2,C] (modules.py:614-622)
 void center_crop(Ctx& c, const void* x, void* y, int B, int P, int C);
 
-// ---- K1: fused window-MSA on tcgen05 (tc_wmsa.cu), bf16, C = 96 / 3 heads / window 8 ----------------
+// ---- K1: fused window-MSA on tcgen05 (tc_wmsa.cu), bf16, C = 96 / 3 heads or C = 192 / 6 heads, window 8 ----
 bool tc_wmsa_supported(int B, int H, int W, int C, int heads, int ws, int shift);
-// out[token] = x[token] + proj(window_attention(norm1(x)))  for x, out bf16 [B, H*W, 96]; mean/rstd = norm1 stats of x
+// out[token] = x[token] + proj(window_attention(norm1(x)))  for x, out bf16 [B, H*W, C]; mean/rstd = norm1 stats of x
 // mean2/rstd2 (optional): LayerNorm statistics (eps 1e-5) of the output rows, for norm2
 void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
-             int H, int W, int shift, float* mean2, float* rstd2);
+             int H, int W, int C, int shift, float* mean2, float* rstd2);
 
 // two independent problems of the same geometry in one launch (the encoder's flow and raster branches in lock step)
 void tc_wmsa_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],

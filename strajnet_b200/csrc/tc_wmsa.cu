@@ -33,27 +33,35 @@ namespace {
 
 using namespace tc;
 
-constexpr int C = 96, NH = 3, NTHREADS = 192;
+constexpr int NTHREADS = 192;
 constexpr int X_CHUNK = 128 * 64;         // 8 KB: 128 rows x 32 channels
 constexpr int WQ_CHUNK = 96 * 64;         // 6 KB: (q|k|v of one head) x 32 channels
-constexpr int WP_TILE = 96 * 64;          // 6 KB: proj rows x 32 channels of one head
 constexpr int QKV_TILE = 128 * 64;        // 8 KB: 128 rows x 32 dims
 constexpr int P_CHUNK = 128 * 128;        // 16 KB: 128 rows x 64 keys
-constexpr int OFF_X = 0;
-constexpr int OFF_WQ = OFF_X + 3 * X_CHUNK;
-constexpr int OFF_WP = OFF_WQ + 3 * WQ_CHUNK;
-constexpr int OFF_Q = OFF_WP + WP_TILE;
-constexpr int OFF_K = OFF_Q + QKV_TILE;
-constexpr int OFF_V = OFF_K + QKV_TILE;
-constexpr int OFF_P = OFF_V + QKV_TILE;               // 72 KB: 1024-aligned for the 128-byte swizzle
-constexpr int OFF_AO = OFF_Q;                         // O_h aliases q_h (dead once S_h has been computed)
-constexpr int OFF_TBL = OFF_P + 2 * P_CHUNK;          // float [NH][228]
-constexpr int OFF_LN = OFF_TBL + NH * 228 * 4;        // float colsum[288], biasf[288]
-constexpr int OFF_RID = OFF_LN + 2 * 288 * 4;         // int [128]
-constexpr int OFF_BAR = (OFF_RID + 128 * 4 + 63) & ~63;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(OFF_P % 1024 == 0, "P tile alignment");
-static_assert(2 * (SMEM_BYTES + 1024 + 1024) <= 228 * 1024, "two CTAs per SM");
+// shared-memory plan for C channels (NH = C / 32 heads, K of the QKV GEMM in NC = C / 32 chunks)
+template <int C>
+struct Plan {
+  static constexpr int NH = C / 32, NC = C / 32;
+  static constexpr int WP_TILE = C * 64;  // proj rows x 32 channels of one head
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_WQ = OFF_X + NC * X_CHUNK;
+  static constexpr int OFF_WP = OFF_WQ + NC * WQ_CHUNK;
+  static constexpr int OFF_Q = OFF_WP + WP_TILE;
+  static constexpr int OFF_K = OFF_Q + QKV_TILE;
+  static constexpr int OFF_V = OFF_K + QKV_TILE;
+  static constexpr int OFF_P = OFF_V + QKV_TILE;       // 1024-aligned for the 128-byte swizzle
+  static constexpr int OFF_AO = OFF_Q;                 // O_h aliases q_h (dead once S_h has been computed)
+  static constexpr int OFF_TBL = OFF_P + 2 * P_CHUNK;  // float [NH][228]
+  static constexpr int OFF_LN = OFF_TBL + NH * 228 * 4;  // float colsum[3C], biasf[3C]
+  static constexpr int OFF_RID = OFF_LN + 2 * 3 * C * 4;  // int [128]
+  static constexpr int OFF_BAR = (OFF_RID + 128 * 4 + 63) & ~63;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 128 + C <= 256 ? 256 : 512;  // region A (128) + the proj accumulator (C)
+  static constexpr int CTAS_PER_SM = C == 96 ? 2 : 1;
+  static_assert(OFF_P % 1024 == 0, "P tile alignment");
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024 + 1024) <= 228 * 1024, "shared memory per SM");
+  static_assert(128 + C <= 512 && C % 32 == 0 && C <= 256, "one proj MMA (N = C <= 256), TMEM budget");
+};
 constexpr float QSCALE = 0.17677669529663687f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -98,8 +106,14 @@ __device__ __forceinline__ void store_row64(uint8_t* tile, int r, const float* v
     *reinterpret_cast<uint4*>(tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = pack8(v + 8 * j);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int C>
+__global__ void __launch_bounds__(NTHREADS, Plan<C>::CTAS_PER_SM)
 tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
+  using PL = Plan<C>;
+  constexpr int NH = PL::NH, NC = PL::NC, WP_TILE = PL::WP_TILE;
+  constexpr int OFF_X = PL::OFF_X, OFF_WQ = PL::OFF_WQ, OFF_WP = PL::OFF_WP, OFF_Q = PL::OFF_Q, OFF_K = PL::OFF_K;
+  constexpr int OFF_V = PL::OFF_V, OFF_P = PL::OFF_P, OFF_AO = PL::OFF_AO, OFF_TBL = PL::OFF_TBL, OFF_LN = PL::OFF_LN;
+  constexpr int OFF_RID = PL::OFF_RID, OFF_BAR = PL::OFF_BAR;
   // group of this CTA: CTAs [0, pp.g[0].ctas) run group 0, the rest group 1 (same shapes, other tensors: the flow / raster
   // branches of the encoder in lock step).  Both parameter sets sit in one array so that the choice is a constant-bank
   // offset, not a select per field.
@@ -126,13 +140,13 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
     for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, PL::TMEM_COLS);
   // constants: bias table (pre-multiplied by log2 e), LayerNorm-fold vectors; zero the P tile once (the
   // cross-window halves are never written again)
   for (int i = threadIdx.x; i < NH * 225; i += NTHREADS) tbl[(i % NH) * 228 + i / NH] = p.table[i] * LOG2E;
-  for (int i = threadIdx.x; i < 288; i += NTHREADS) {
+  for (int i = threadIdx.x; i < 3 * C; i += NTHREADS) {
     lnc[i] = p.colsum[i];
-    lnc[288 + i] = p.biasf[i];
+    lnc[3 * C + i] = p.biasf[i];
   }
   for (int i = threadIdx.x; i < 2 * P_CHUNK / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(smem + OFF_P)[i] = make_uint4(0, 0, 0, 0);
@@ -150,12 +164,12 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
       uint32_t it = 0, hc = 0;
       for (int tile = cta; tile < p.num_tiles; tile += nctas, ++it) {
         mbar_wait(&bar[B_XEMPTY], (it & 1) ^ 1);
-        mbar_expect_tx(&bar[B_XFULL], 3 * X_CHUNK);
+        mbar_expect_tx(&bar[B_XFULL], NC * X_CHUNK);
         for (int wt = 0; wt < 2; ++wt) {
           const int gw = 2 * tile + wt, b = gw / p.nW, wl = gw % p.nW, wi = wl / p.wpr, wj = wl % p.wpr;
           for (int quad = 0; quad < 4; ++quad) {
             const int yq = (2 * wi + (quad >> 1) + s4) % hq, xq = (2 * wj + (quad & 1) + s4) % wq;
-            for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < NC; ++c)
               tma_load_5d(smem + OFF_X + c * X_CHUNK + (wt * 64 + quad * 16) * 64, mapX, &bar[B_XFULL], c * 32, 0, xq,
                           0, b * hq + yq);
           }
@@ -163,8 +177,8 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
         // weights of each head: the slots are released by the MMA warp as soon as the MMAs reading them have completed
         for (int h = 0; h < NH; ++h, ++hc) {
           mbar_wait(&bar[B_WQEMPTY], (hc & 1) ^ 1);
-          mbar_expect_tx(&bar[B_WQFULL], 3 * WQ_CHUNK);
-          for (int c = 0; c < 3; ++c)
+          mbar_expect_tx(&bar[B_WQFULL], NC * WQ_CHUNK);
+          for (int c = 0; c < NC; ++c)
             for (int part = 0; part < 3; ++part)
               tma_load_2d(smem + OFF_WQ + c * WQ_CHUNK + part * 32 * 64, mapWq, &bar[B_WQFULL], c * 32, part * C + h * 32);
           mbar_wait(&bar[B_WPEMPTY], (hc & 1) ^ 1);
@@ -176,7 +190,7 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
   } else if (warp == 1) {
     // the whole warp runs the loop (uniform control flow); one elected lane issues each batch of MMAs
     constexpr uint32_t HI128 = desc_hi(128, 1024), HI64 = desc_hi(64, 512);
-    const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, 128);
+    const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, 128), id_proj = make_idesc_bf16(128, C);
     const uint32_t id_pv = make_idesc_bf16(128, 32) | (1u << 16);  // B (= v_h) is MN-major
     const uint32_t x_lo = desc_lo(smem_u32(smem + OFF_X)), wq_lo = desc_lo(smem_u32(smem + OFF_WQ));
     const uint32_t wp_lo = desc_lo(smem_u32(smem + OFF_WP)), q_lo = desc_lo(smem_u32(smem + OFF_Q));
@@ -192,7 +206,7 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < 6; ++s) {  // K = 96: three 32-channel chunks x two K steps
+          for (int s = 0; s < 2 * NC; ++s) {  // K = C: 32-channel chunks x two K steps
             const uint32_t c = s >> 1, k = s & 1;
             umma_bf16_w(tmem_a, x_lo + (c * X_CHUNK >> 4) + 2 * k, HI64, wq_lo + (c * WQ_CHUNK >> 4) + 2 * k, HI64, id_qkv,
                         s != 0);
@@ -227,7 +241,7 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            umma_bf16_w(tmem_proj, ao_lo + 2 * k, HI64, wp_lo + 2 * k, HI64, id_qkv, (h | k) != 0);
+            umma_bf16_w(tmem_proj, ao_lo + 2 * k, HI64, wp_lo + 2 * k, HI64, id_proj, (h | k) != 0);
           umma_commit(&bar[B_WPEMPTY]);
           if (h == NH - 1) umma_commit(&bar[B_PROJ]);
         }
@@ -264,7 +278,7 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
           float v[32];
           tmem_ld32(tmem_a + lane_addr + part * 32, v);
           const float* cs = lnc + part * C + h * 32;
-          const float* bf = lnc + 288 + part * C + h * 32;
+          const float* bf = lnc + 3 * C + part * C + h * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float t = rstd * (v[i] - mean * cs[i]) + bf[i];
@@ -370,21 +384,22 @@ tc_wmsa_kernel(const __grid_constant__ PairMaps maps, const WmsaPPair pp) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_a, 256);
+    tmem_dealloc(tmem_a, PL::TMEM_COLS);
   }
 }
 
 }  // namespace
 
 bool tc_wmsa_supported(int B, int H, int W, int Cc, int heads, int ws, int shift) {
-  if (Cc != C || heads != NH || ws != 8 || (shift != 0 && shift != 4)) return false;
+  if ((Cc != 96 && Cc != 192) || heads * 32 != Cc || ws != 8 || (shift != 0 && shift != 4)) return false;
   if (H % 8 || W % 8 || H < 8 || W < 8) return false;
   return ((long long)B * (H / 8) * (W / 8)) % 2 == 0;
 }
 
 // x, out: bf16 [B, H*W, 96]; mean/rstd: fp32 [B*H*W] (norm1 statistics of x); w: norm1-folded qkv (tensor-core copy).
 // groups = 2: two independent problems of the same geometry in ONE launch (half of the CTAs each)
-static void tc_wmsa_launch(Ctx& c, int groups, const void* const* x, void* const* out, const float* const* mean,
+template <int C>
+static void tc_wmsa_launch_c(Ctx& c, int groups, const void* const* x, void* const* out, const float* const* mean,
                            const float* const* rstd, const SjSwinBlockW* const* w, int B, int H, int W, int shift,
                            float* const* mean2, float* const* rstd2) {
   if (!c.ok() || c.dry) return;
@@ -393,7 +408,7 @@ static void tc_wmsa_launch(Ctx& c, int groups, const void* const* x, void* const
   WmsaPPair ppair = {};
   WmsaP (&pp)[2] = ppair.g;
   const int tiles = B * (H / 8) * (W / 8) / 2;
-  const int cap = 2 * num_sms() / groups;  // two CTAs per SM
+  const int cap = Plan<C>::CTAS_PER_SM * num_sms() / groups;
   const int per = tiles < cap ? tiles : cap;
   for (int g = 0; g < groups; ++g) {
     const SjSwinBlockW& wg = *w[g];
@@ -408,7 +423,7 @@ static void tc_wmsa_launch(Ctx& c, int groups, const void* const* x, void* const
     uint64_t sq[1] = {(uint64_t)C * 2};
     uint32_t bq[2] = {32, 32};
     uint64_t dp[2] = {(uint64_t)C, (uint64_t)C};
-    uint32_t bp[2] = {32, 96};
+    uint32_t bp[2] = {32, (uint32_t)C};
     if (!encode_tmap(&maps[g][0], x[g], 5, dx, sx, bx, 64) || !encode_tmap(&maps[g][1], wg.qkv_ln.w_tc, 2, dq, sq, bq, 64) ||
         !encode_tmap(&maps[g][2], wg.proj.w_tc, 2, dp, sq, bp, 64)) {
       snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (tc_wmsa)");
@@ -427,24 +442,32 @@ static void tc_wmsa_launch(Ctx& c, int groups, const void* const* x, void* const
     pp[1] = pp[0];
     for (int i = 0; i < 3; ++i) maps[1][i] = maps[0][i];
   }
-  const size_t smem = 1024 + SMEM_BYTES;
-  if (!SJ_SMEM_LIMIT_OK((tc_wmsa_kernel), 227 * 1024)) {
+  const size_t smem = 1024 + Plan<C>::SMEM_BYTES;
+  if (!SJ_SMEM_LIMIT_OK((tc_wmsa_kernel<C>), 227 * 1024)) {
     c.fail(SJ_ECUDA);
     return;
   }
-  SJ_LAUNCH(c, "tc_wmsa", tc_wmsa_kernel, groups * per, NTHREADS, smem, pm, ppair);
+  SJ_LAUNCH(c, "tc_wmsa", tc_wmsa_kernel<C>, groups * per, NTHREADS, smem, pm, ppair);
+}
+
+static void tc_wmsa_launch(Ctx& c, int Cc, int groups, const void* const* x, void* const* out, const float* const* mean,
+                           const float* const* rstd, const SjSwinBlockW* const* w, int B, int H, int W, int shift,
+                           float* const* mean2, float* const* rstd2) {
+  if (Cc == 96) tc_wmsa_launch_c<96>(c, groups, x, out, mean, rstd, w, B, H, W, shift, mean2, rstd2);
+  else if (Cc == 192) tc_wmsa_launch_c<192>(c, groups, x, out, mean, rstd, w, B, H, W, shift, mean2, rstd2);
+  else c.fail(SJ_EUNSUPPORTED);
 }
 
 void tc_wmsa(Ctx& c, const void* x, void* out, const float* mean, const float* rstd, const SjSwinBlockW& w, int B,
-             int H, int W, int shift, float* mean2, float* rstd2) {
+             int H, int W, int Cc, int shift, float* mean2, float* rstd2) {
   const SjSwinBlockW* wp = &w;
-  tc_wmsa_launch(c, 1, &x, &out, &mean, &rstd, &wp, B, H, W, shift, &mean2, &rstd2);
+  tc_wmsa_launch(c, Cc, 1, &x, &out, &mean, &rstd, &wp, B, H, W, shift, &mean2, &rstd2);
 }
 
 void tc_wmsa_pair(Ctx& c, const void* const x[2], void* const out[2], const float* const mean[2], const float* const rstd[2],
                   const SjSwinBlockW* const w[2], int B, int H, int W, int shift, float* const mean2[2],
                   float* const rstd2[2]) {
-  tc_wmsa_launch(c, 2, x, out, mean, rstd, w, B, H, W, shift, mean2, rstd2);
+  tc_wmsa_launch(c, 96, 2, x, out, mean, rstd, w, B, H, W, shift, mean2, rstd2);
 }
 
 }  // namespace sj
