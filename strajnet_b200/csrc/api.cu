@@ -168,9 +168,11 @@ bool swin_block_impl(Ctx& c, const void* x, void* y, const SjSwinBlockW& w, int 
 }
 
 // ---- PatchMerging.call (modules.py:274-292) -----------------------------------------------------
-void patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, const void* add, int B, int H, int W,
-                        int C) {
-  if (H % 2 || W % 2 || C % 16) { c.fail(SJ_EUNSUPPORTED); return; }
+// out_mean / out_rstd (optional): where the eps-1e-5 LayerNorm statistics of the output rows go when the GEMM epilogue can
+// produce them (tensor-core path, one n-tile covering the 2C outputs); returns whether they were written
+bool patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, const void* add, int B, int H, int W,
+                        int C, float* out_mean = nullptr, float* out_rstd = nullptr) {
+  if (H % 2 || W % 2 || C % 16) { c.fail(SJ_EUNSUPPORTED); return false; }
   const int M = B * (H / 2) * (W / 2);
   size_t mark = c.ws.mark();
   float* mean = (float*)c.alloc((size_t)M * 4);
@@ -181,8 +183,12 @@ void patch_merging_impl(Ctx& c, const void* x, void* y, const SjPatchMergeW& w, 
   g.set_weights(w.reduction); g.ldw = 2 * C; g.C = y; g.ldc = 2 * C; g.M = M; g.N = 2 * C; g.K = 4 * C;
   g.ln_mean = mean; g.ln_rstd = rstd; g.ln_g = w.norm.g; g.ln_b = w.norm.b;
   g.R = add; g.ldr = 2 * C;
+  static const bool stats_off = getenv("SJ_DISABLE_FUSED_STATS") != nullptr;
+  const bool wrote = out_mean && out_rstd && c.dtype == SJ_BF16 && w.reduction.w_tc && !stats_off && tc_gemm_stats_ok(2 * C);
+  if (wrote) { g.st_mean = out_mean; g.st_rstd = out_rstd; g.st_eps = 1e-5f; }
   gemm(c, g);
   c.ws.release(mark);
+  return wrote;
 }
 
 // ---- BasicLayer.call (modules.py:351-364) -------------------------------------------------------
@@ -283,6 +289,10 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
                  tc_mlp96_supported(96, 384, lf.blocks_host[i]) && tc_mlp96_supported(96, 384, l0.blocks_host[i]);
   void* x1 = c.alloc_act(B * L0 / 4 * 2 * E);
   void* x2 = c.alloc_act(B * L0 / 16 * 4 * E);
+  // norm1 statistics of layer 1's input, out of the patch-merging epilogue of layer 0 (lock-step path)
+  float* x1_mean = (float*)c.alloc((size_t)B * L0 / 4 * 4);
+  float* x1_rstd = (float*)c.alloc((size_t)B * L0 / 4 * 4);
+  bool x1_stats = false;
   if (lockstep) {
     const size_t ntok = (size_t)B * L0;
     void* xm = c.alloc_act(ntok * E);                      // raster-branch tokens (f0 holds the flow branch)
@@ -329,7 +339,7 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
       cr_[0] = nr[0]; cr_[1] = nr[1];
     }
     patch_merging_impl(c, full[0], flow_x, lf.down, nullptr, B, P, P, 96);
-    patch_merging_impl(c, full[1], x1, l0.down, flow_x, B, P, P, 96);  // + flow_x (modules.py:613)
+    x1_stats = patch_merging_impl(c, full[1], x1, l0.down, flow_x, B, P, P, 96, x1_mean, x1_rstd);  // + flow_x (modules.py:613)
   } else {
   if (pe_fused) {
     tc_patch_embed(c, flow, IN_F32, S, 2, 1, w.pe_flow, nullptr, 0, 0, 0, nullptr, 0, w.flow_norm, B, f0, pe_mean, pe_rstd);
@@ -372,7 +382,8 @@ void encoder_impl(Ctx& c, const void* ogm, const void* map_img, const float* flo
   basic_layer_impl(c, x0, x1, full[1], w.layers[0], flow_x, B, P, P, 8, pe_stats ? pe_mean : nullptr,
                    pe_stats ? pe_rstd : nullptr);  // + flow_x (modules.py:613)
   }
-  basic_layer_impl(c, x1, x2, full[2], w.layers[1], nullptr, B, P / 2, P / 2, 8);
+  basic_layer_impl(c, x1, x2, full[2], w.layers[1], nullptr, B, P / 2, P / 2, 8, x1_stats ? x1_mean : nullptr,
+                   x1_stats ? x1_rstd : nullptr);
   basic_layer_impl(c, x2, nullptr, full[3], w.layers[2], nullptr, B, P / 4, P / 4, 8);
   if (large) {  // centre crops (modules.py:614-622)
     center_crop(c, full[0], outs[0], B, P, E);
