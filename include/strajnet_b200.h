@@ -104,6 +104,9 @@ typedef struct {
   const float* offproj2_b; /* [384] */
   const float* rpe_table;  /* [31,31,8]                                               FG_MSA.py:70    */
   SjLinear out;            /* proj_out [384,384] + [384]                              FG_MSA.py:64    */
+  const void* conv0_w_tc;  /* bf16 copy of conv0_w in mma.m16n8k16 B-fragment order, or NULL (bf16 path then converts conv0_w
+                            * on the fly): [8 groups][9 taps][3 k-steps][3 n-pairs][32 lanes][8] with, for lane = 4*g + t and
+                            * n-tile nt = 2*pair + (e>>2): element e&3 = conv0_w[tap][16*ks + 2*t + {0,1,8,9}[e&3]][48*group + 8*nt + g] */
 } SjFgmsaW;
 
 /* TrajNetCrossAttention (trajNet.py:236-319) = TrajNet (:91-187) + 8x Cross_AttentionT (:189-234).

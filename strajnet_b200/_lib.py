@@ -55,7 +55,7 @@ class SjEncoderW(C.Structure):
 class SjFgmsaW(C.Structure):
     _fields_ = [("qkv", SjLinear), ("conv0_w", c_fp), ("conv0_b", c_fp), ("conv_norm", SjNorm),
                 ("offproj_w", c_fp), ("offproj2_w", c_fp), ("offproj2_b", c_fp), ("rpe_table", c_fp),
-                ("out", SjLinear)]
+                ("out", SjLinear), ("conv0_w_tc", C.c_void_p)]
 
 
 class SjTrajW(C.Structure):

@@ -782,7 +782,7 @@ using namespace sj;
 
 extern "C" {
 
-int sj_version(void) { return 101; }
+int sj_version(void) { return 102; }
 
 size_t sj_sizeof(int which) {
   switch (which) {

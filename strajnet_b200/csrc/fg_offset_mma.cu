@@ -3,8 +3,9 @@
 // (FG_MSA.py:84-92, :114-117, :134).  1.4 GFLOP per batch-16 step, but the CUDA-core kernel re-reads the 663 KB of
 // conv weights for every 8 pixels; here one block owns two image rows (32 pixels = two m16 tiles), warp g owns
 // group g (N = 48, K = 9 taps x 48 channels) and runs it as 324 mma.sync.m16n8k16 with the activation halo
-// (4 x 18 pixels x 384 channels) staged once in shared memory and read with ldmatrix; the fp32 weights are
-// converted to bf16 fragments on the fly (each fragment serves both pixel tiles).
+// (4 x 18 pixels x 384 channels) staged once in shared memory and read with ldmatrix; the weights come as bf16
+// B fragments packed on the host side (one coalesced 16-byte load per lane for four MMAs), or, without that copy, as
+// fp32 converted on the fly (each fragment serves both pixel tiles).
 #include "kernels.h"
 #include "mma_sync.cuh"
 
@@ -46,6 +47,31 @@ __global__ void __launch_bounds__(256) fg_offset_mma_kernel(const bf16* __restri
   const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(qs);
   // ldmatrix lane addressing for the A operand: tiles (pixels +0, k +0), (pixels +8, k +0), (pixels +0, k +8), (pixels +8, k +8)
   const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_k = (lane >> 4) * 8;
+  if (w.conv0_w_tc) {
+    // bf16 weights already in B-fragment order (weights.py: fg_conv_fragments): one 16-byte load per lane feeds two
+    // n-tiles x two pixel tiles = four MMAs
+    const uint4* wf = reinterpret_cast<const uint4*>(w.conv0_w_tc) + (long long)grp * (9 * 3 * 3 * 32) + lane;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        uint4 bw[3];
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) bw[pr] = __ldg(wf + ((tap * 3 + ks) * 3 + pr) * 32);
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          ldsm_x4(a[mt], qs_base + (uint32_t)((((mt + dy) * 18 + a_pix + dx) * PS + grp * 48 + ks * 16 + a_k) * 2));
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+          mma_bf16(acc[0][2 * pr], a[0], bw[pr].x, bw[pr].y);
+          mma_bf16(acc[1][2 * pr], a[1], bw[pr].x, bw[pr].y);
+          mma_bf16(acc[0][2 * pr + 1], a[0], bw[pr].z, bw[pr].w);
+          mma_bf16(acc[1][2 * pr + 1], a[1], bw[pr].z, bw[pr].w);
+        }
+      }
+    }
+  } else {
   for (int tap = 0; tap < 9; ++tap) {
     const int dy = tap / 3, dx = tap % 3;
     const float* wt = w.conv0_w + (long long)tap * 48 * 384 + grp * 48;  // [cc][n], n contiguous (stride 384)
@@ -63,6 +89,7 @@ __global__ void __launch_bounds__(256) fg_offset_mma_kernel(const bf16* __restri
         mma_bf16(acc[1][nt], a[1], b0, b1);
       }
     }
+  }
   }
   // thread holds, for pixels (mt, g8) and (mt, g8 + 8), channels grp*48 + nt*8 + 2t + {0,1}
   float s4[4] = {0.f, 0.f, 0.f, 0.f};  // pixel index p = mt*2 + half -> pixel mt*16 + g8 + 8*half

@@ -166,6 +166,18 @@ def fgmsa_shapes(fg: bool = True) -> Dict[str, tuple]:
     return s
 
 
+def fg_conv_fragments(k: Tensor) -> Tensor:
+    """conv_offset_0 kernel [3,3,48,384] (grouped 3x3, 8 groups of 48 -> 48) in the order the mma.sync kernel reads it
+    (fg_offset_mma.cu): [group][tap][k-step][n-pair][lane][8], lane = 4*g + t, n-tile nt = 2*pair + (e >> 2), element
+    e & 3 = k[tap][16*ks + 2*t + (0, 1, 8, 9)[e & 3]][48*group + 8*nt + g] -- one 16-byte load per lane and n-pair."""
+    w = k.reshape(9, 48, 384)
+    grp, tap, ks, pair, g, t, e = torch.meshgrid(torch.arange(8), torch.arange(9), torch.arange(3), torch.arange(3),
+                                                 torch.arange(8), torch.arange(4), torch.arange(8), indexing="ij")
+    kk = 16 * ks + 2 * t + torch.tensor([0, 1, 8, 9])[e & 3]
+    n = 48 * grp + 8 * (2 * pair + (e >> 2)) + g
+    return w[tap, kk, n].contiguous()          # [8,9,3,3,8,4,8]: (g, t) flatten to lane = 4*g + t
+
+
 def traj_shapes() -> Dict[str, tuple]:
     s = {}
     p = "traj_net.traj_encoder."
@@ -371,6 +383,8 @@ class Packer:
             s.offproj2_b = self.ptr(self.get(p + "conv_offset_proj2.bias"))
         s.rpe_table = self.ptr(self.get(p + "rpe_table"))
         s.out = self.linear(self.get(p + "proj_out.kernel")[0, 0], self.get(p + "proj_out.bias"))
+        if self.tc:
+            s.conv0_w_tc = self.ptr(fg_conv_fragments(self.get(p + "conv_offset_0.kernel")), torch.bfloat16)
         return s
 
     def traj(self, p: str) -> L.SjTrajW:

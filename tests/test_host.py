@@ -160,3 +160,21 @@ def test_output_grid_answers_the_serving_loops_calls():
 def test_numa_binding_is_best_effort():
     from strajnet_b200.parallel import bind_to_local_numa
     assert isinstance(bind_to_local_numa(0), dict)  # no GPU here: {} and no exception
+
+
+def test_fg_conv_fragment_order():
+    """weights.fg_conv_fragments: element (group, tap, k-step, n-pair, lane, e) of the packed copy is the conv kernel entry
+    the mma.m16n8k16 B fragment of fg_offset_mma.cu expects there (FG_MSA.py:51 kernel, [3,3,48,384])."""
+    import torch
+    from strajnet_b200.weights import fg_conv_fragments
+    g = torch.Generator().manual_seed(5)
+    k = torch.randn(3, 3, 48, 384, generator=g)
+    f = fg_conv_fragments(k).reshape(8, 9, 3, 3, 32, 8)
+    w = k.reshape(9, 48, 384)
+    idx = torch.randint(0, 10 ** 6, (400, 6), generator=g)
+    for row in idx.tolist():
+        grp, tap, ks, pr, lane, e = (row[i] % n for i, n in enumerate((8, 9, 3, 3, 32, 8)))
+        gq, t = lane // 4, lane % 4
+        kk = 16 * ks + 2 * t + (0, 1, 8, 9)[e & 3]
+        n = 48 * grp + 8 * (2 * pr + (e >> 2)) + gq
+        assert f[grp, tap, ks, pr, lane, e] == w[tap, kk, n]
