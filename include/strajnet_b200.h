@@ -27,6 +27,7 @@
  *   - sj_probe_start / sj_probe_stop: per-thread timing probe for bench.py;
  *   - environment switches read once at first use, kept so that an earlier kernel generation can be re-measured against
  *     its replacement (each selects between two implementations of the same op): SJ_DISABLE_FUSED_WMSA,
+ *     SJ_WMSA_MAX_C=96 (fused window-MSA for the 96-channel stages only), SJ_DISABLE_FUSED_PE (patch embedding as im2col -> GEMM -> combine),
  *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION, SJ_DISABLE_RESADD2, SJ_DISABLE_LOCKSTEP,
  *     SJ_DISABLE_ATTN_MMA, SJ_DISABLE_IM2COL_STAGED, SJ_DISABLE_NORM_FAST, SJ_DISABLE_FG_OFFSET_MMA (fall back to the
  *     previous kernel), SJ_NO_SIDE_STREAM (keep the trajectory actor branch on the caller's stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue

@@ -51,24 +51,29 @@ __global__ void __launch_bounds__(256) fg_offset_mma_kernel(const bf16* __restri
     // bf16 weights already in B-fragment order (weights.py: fg_conv_fragments): one 16-byte load per lane feeds two
     // n-tiles x two pixel tiles = four MMAs
     const uint4* wf = reinterpret_cast<const uint4*>(w.conv0_w_tc) + (long long)grp * (9 * 3 * 3 * 32) + lane;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3, dx = tap % 3;
+    // 27 (tap, k-step) iterations, fully unrolled with the next iteration's fragments in flight under this one's MMAs
+    // (each load is an L2 round trip; serialised they were most of the kernel)
+    uint4 bw[2][3];
 #pragma unroll
-      for (int ks = 0; ks < 3; ++ks) {
-        uint4 bw[3];
+    for (int pr = 0; pr < 3; ++pr) bw[0][pr] = __ldg(wf + pr * 32);
 #pragma unroll
-        for (int pr = 0; pr < 3; ++pr) bw[pr] = __ldg(wf + ((tap * 3 + ks) * 3 + pr) * 32);
-        uint32_t a[2][4];
+    for (int it = 0; it < 27; ++it) {
+      const int tap = it / 3, ks = it % 3, dy = tap / 3, dx = tap % 3;
+      if (it + 1 < 27) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-          ldsm_x4(a[mt], qs_base + (uint32_t)((((mt + dy) * 18 + a_pix + dx) * PS + grp * 48 + ks * 16 + a_k) * 2));
+        for (int pr = 0; pr < 3; ++pr) bw[(it + 1) & 1][pr] = __ldg(wf + ((it + 1) * 3 + pr) * 32);
+      }
+      uint32_t a[2][4];
 #pragma unroll
-        for (int pr = 0; pr < 3; ++pr) {
-          mma_bf16(acc[0][2 * pr], a[0], bw[pr].x, bw[pr].y);
-          mma_bf16(acc[1][2 * pr], a[1], bw[pr].x, bw[pr].y);
-          mma_bf16(acc[0][2 * pr + 1], a[0], bw[pr].z, bw[pr].w);
-          mma_bf16(acc[1][2 * pr + 1], a[1], bw[pr].z, bw[pr].w);
-        }
+      for (int mt = 0; mt < 2; ++mt)
+        ldsm_x4(a[mt], qs_base + (uint32_t)((((mt + dy) * 18 + a_pix + dx) * PS + grp * 48 + ks * 16 + a_k) * 2));
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        const uint4 b = bw[it & 1][pr];
+        mma_bf16(acc[0][2 * pr], a[0], b.x, b.y);
+        mma_bf16(acc[1][2 * pr], a[1], b.x, b.y);
+        mma_bf16(acc[0][2 * pr + 1], a[0], b.z, b.w);
+        mma_bf16(acc[1][2 * pr + 1], a[1], b.z, b.w);
       }
     }
   } else {
