@@ -43,6 +43,36 @@ NUM_WAYPOINTS = 8
 
 
 # --------------------------------------------------------------------------
+# bf16 storage emulation (off by default: the oracle is the fp32 / fp64 restatement)
+# --------------------------------------------------------------------------
+# Inside `with bf16_storage():` the same graph is evaluated with the rounding points of the benchmarked CUDA path modelled
+# at LAYER granularity: every Dense / Conv / tfa-MHA kernel is rounded to bf16 (the tensor-core copies), and every tensor
+# that path stores in HBM or feeds to a tensor core as an operand (layer outputs after their activation, residual sums,
+# q / k / v, attention outputs) is rounded to bf16; accumulation, LayerNorm, softmax and bias adds stay in the working
+# precision.  It is NOT a bit-level model of the kernels (LayerNorm folding, sub-pixel tap folding, un-normalised bf16
+# softmax weights are not modelled: tests/test_gpu_kernels.py does that per kernel); it removes the systematic part of the
+# bf16-vs-fp32 gap so that the whole-forward gate can sit at rounding-noise level instead of at 8 % of the logit range.
+_EMULATE_BF16 = False
+
+
+class bf16_storage:
+    def __enter__(self):
+        global _EMULATE_BF16
+        self.prev, _EMULATE_BF16 = _EMULATE_BF16, True
+        return self
+
+    def __exit__(self, *exc):
+        global _EMULATE_BF16
+        _EMULATE_BF16 = self.prev
+        return False
+
+
+def _st(x: Tensor) -> Tensor:
+    """a stored activation / tensor-core operand of the bf16 path"""
+    return x.to(torch.bfloat16).to(x.dtype) if _EMULATE_BF16 else x
+
+
+# --------------------------------------------------------------------------
 # elementwise / small helpers
 # --------------------------------------------------------------------------
 def gelu_tanh(x: Tensor) -> Tensor:
@@ -57,21 +87,24 @@ def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
     return (x - mu) / torch.sqrt(var + eps) * gamma + beta
 
 
-def dense(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None) -> Tensor:
-    y = x @ kernel
-    return y if bias is None else y + bias
+def dense(x: Tensor, kernel: Tensor, bias: Optional[Tensor] = None, store: bool = True) -> Tensor:
+    """store=False: the result is consumed in the producing epilogue (activation / residual) before it is stored"""
+    y = x @ _st(kernel)
+    y = y if bias is None else y + bias
+    return _st(y) if store else y
 
 
 def conv2d_nhwc(x: Tensor, kernel: Tensor, bias: Optional[Tensor], stride: int = 1,
-                padding: str = "valid", groups: int = 1) -> Tensor:
+                padding: str = "valid", groups: int = 1, store: bool = True) -> Tensor:
     """Keras Conv2D on [N,H,W,C] with kernel [kh,kw,cin/groups,cout]; 'same' = TF SAME (odd k, stride 1)."""
-    w = kernel.permute(3, 2, 0, 1)
+    w = _st(kernel).permute(3, 2, 0, 1)
     pad = 0
     if padding == "same":
         assert stride == 1 and kernel.shape[0] % 2 == 1
         pad = kernel.shape[0] // 2
     y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride=stride, padding=pad, groups=groups)
-    return y.permute(0, 2, 3, 1)
+    y = y.permute(0, 2, 3, 1)
+    return _st(y) if store else y
 
 
 # --------------------------------------------------------------------------
@@ -128,8 +161,8 @@ def window_attention(xw: Tensor, w: Weights, p: str, num_heads: int, ws: int,
         attn = attn.reshape(-1, nW, num_heads, N, N) + mask.to(attn.dtype)[None, :, None]
         attn = attn.reshape(-1, num_heads, N, N)
     attn = torch.softmax(attn, dim=-1)
-    x = (attn @ v).permute(0, 2, 1, 3).reshape(B_, N, C)
-    return dense(x, w[p + "proj.kernel"], w[p + "proj.bias"])
+    x = _st((attn @ v).permute(0, 2, 1, 3).reshape(B_, N, C))
+    return dense(x, w[p + "proj.kernel"], w[p + "proj.bias"], store=False)
 
 
 def swin_block(x: Tensor, w: Weights, p: str, H: int, W: int, num_heads: int, ws: int, shift: int) -> Tensor:
@@ -150,10 +183,10 @@ def swin_block(x: Tensor, w: Weights, p: str, H: int, W: int, num_heads: int, ws
     y = window_reverse(aw.reshape(-1, ws, ws, C), ws, H, W, C)
     if shift > 0:
         y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
-    x = shortcut + y.reshape(B, L, C)
+    x = _st(shortcut + y.reshape(B, L, C))
     h = layer_norm(x, w[p + "norm2.gamma"], w[p + "norm2.beta"], 1e-5)
-    h = gelu_tanh(dense(h, w[p + "mlp.fc1.kernel"], w[p + "mlp.fc1.bias"]))
-    return x + dense(h, w[p + "mlp.fc2.kernel"], w[p + "mlp.fc2.bias"])
+    h = _st(gelu_tanh(dense(h, w[p + "mlp.fc1.kernel"], w[p + "mlp.fc1.bias"], store=False)))
+    return _st(x + dense(h, w[p + "mlp.fc2.kernel"], w[p + "mlp.fc2.bias"], store=False))
 
 
 def patch_merging(x: Tensor, w: Weights, p: str, H: int, W: int) -> Tensor:
@@ -169,7 +202,7 @@ def patch_merging(x: Tensor, w: Weights, p: str, H: int, W: int) -> Tensor:
 
 def patch_embed(x: Tensor, w: Weights, p: str) -> Tensor:
     """modules.py:437-446: Conv2D k=4 s=4 VALID + bias -> flatten -> LN(1e-5)."""
-    y = conv2d_nhwc(x, w[p + "proj.kernel"], w[p + "proj.bias"], stride=4)
+    y = conv2d_nhwc(_st(x), w[p + "proj.kernel"], w[p + "proj.bias"], stride=4, store=False)
     B, Hp, Wp, E = y.shape
     return layer_norm(y.reshape(B, Hp * Wp, E), w[p + "norm.gamma"], w[p + "norm.beta"], 1e-5)
 
@@ -195,7 +228,7 @@ def encoder_forward(ogm: Tensor, map_img: Tensor, flow: Tensor, w: Weights, cfg:
     nl = len(depths)
     vec = ogm[..., 0]  # :572 (ogm[...,1] is never used, Q4)
     f = patch_embed(flow, w, p + "patch_embed_flow.")
-    f = layer_norm(f, w[p + "flow_norm.gamma"], w[p + "flow_norm.beta"], 1e-5)
+    f = _st(layer_norm(f, w[p + "flow_norm.gamma"], w[p + "flow_norm.beta"], 1e-5))
     flow_x, flow_res = basic_layer(f, w, p + "flow_layer.", P, P, depths[0], heads[0], ws, nl > 1)
     if not large_input:
         x = patch_embed(vec, w, p + "patch_embed_vecicle.") + patch_embed(map_img, w, p + "patch_embed_map.")
@@ -203,7 +236,7 @@ def encoder_forward(ogm: Tensor, map_img: Tensor, flow: Tensor, w: Weights, cfg:
         maps = patch_embed(map_img, w, p + "patch_embed_map.").reshape(-1, 64, 64, E)
         maps = F.pad(maps, (0, 0, 32, 32, 32, 32)).reshape(-1, 128 * 128, E)
         x = patch_embed(vec, w, p + "patch_embed_vecicle.") + maps
-    x = layer_norm(x, w[p + "all_patch_norm.gamma"], w[p + "all_patch_norm.beta"], 1e-5)
+    x = _st(layer_norm(x, w[p + "all_patch_norm.gamma"], w[p + "all_patch_norm.beta"], 1e-5))
     res_list = []
     for i in range(nl):
         Hi = P // (2 ** i)
@@ -211,7 +244,7 @@ def encoder_forward(ogm: Tensor, map_img: Tensor, flow: Tensor, w: Weights, cfg:
         if i == nl - 1:
             res = res.reshape(-1, Hi, Hi, res.shape[-1])
         if i == 0:
-            x = x + flow_x
+            x = _st(x + flow_x)
             if large_input:
                 flow_res = flow_res.reshape(-1, 128, 128, E)[:, 32:96, 32:96, :].reshape(-1, 64 * 64, 96)
             res_list.append(flow_res)
@@ -318,9 +351,9 @@ def tfa_mha(query: Tensor, key: Tensor, value: Tensor, w: Weights, p: str, mask:
     Wq, Wk, Wv = w[p + "query_kernel"], w[p + "key_kernel"], w[p + "value_kernel"]
     Wp, bp = w[p + "projection_kernel"], w[p + "projection_bias"]
     hs = Wq.shape[-1]
-    Q = torch.einsum("...ni,hio->...nho", query, Wq)
-    K = torch.einsum("...mi,hio->...mho", key, Wk)
-    V = torch.einsum("...mi,hio->...mho", value, Wv)
+    Q = _st(torch.einsum("...ni,hio->...nho", query, _st(Wq)))
+    K = _st(torch.einsum("...mi,hio->...mho", key, _st(Wk)))
+    V = _st(torch.einsum("...mi,hio->...mho", value, _st(Wv)))
     Q = Q / math.sqrt(float(hs))
     logits = torch.einsum("...nho,...mho->...hnm", Q, K)
     if mask is not None:
@@ -332,8 +365,8 @@ def tfa_mha(query: Tensor, key: Tensor, value: Tensor, w: Weights, p: str, mask:
         masked = (logits.to(torch.float32) + (-10e9)).to(query.dtype)
         logits = torch.where(m.bool().expand_as(logits), logits, masked)
     attn = torch.softmax(logits, dim=-1)
-    out = torch.einsum("...hnm,...mhi->...nhi", attn, V)
-    return torch.einsum("...nhi,hio->...no", out, Wp) + bp
+    out = _st(torch.einsum("...hnm,...mhi->...nhi", attn, V))
+    return _st(torch.einsum("...nhi,hio->...no", out, _st(Wp)) + bp)
 
 
 def elu(x: Tensor) -> Tensor:
@@ -356,7 +389,7 @@ def cross_attention_block(query: Tensor, key: Tensor, mask: Tensor, w: Weights, 
     """trajNet.py:79-87 and :224-234 (same structure; no residual inside)."""
     v = tfa_mha(query, key, key, w, p + "mha.", mask)
     v = layer_norm(v, w[p + "norm1.gamma"], w[p + "norm1.beta"], 1e-3)
-    v = elu(dense(v, w[p + "FFN1.kernel"], w[p + "FFN1.bias"]))
+    v = _st(elu(dense(v, w[p + "FFN1.kernel"], w[p + "FFN1.bias"], store=False)))
     v = dense(v, w[p + "FFN2.kernel"], w[p + "FFN2.bias"])
     return layer_norm(v, w[p + "norm2.gamma"], w[p + "norm2.beta"], 1e-3)
 
@@ -396,7 +429,7 @@ def trajnet_cross_attention(pic_encode: Tensor, obs_traj: Tensor, occ_traj: Tens
     res = []
     for t in range(T):
         o = cross_attention_block(flat[:, t], key, amask, w, f"{p}cross_attn_obs.{t}.")
-        res.append(o + flat[:, t])
+        res.append(_st(o + flat[:, t]))
     return torch.stack(res, 1).reshape(B, T, H, W, D)
 
 
@@ -411,9 +444,9 @@ def _up2(x: Tensor) -> Tensor:
 def _conv_elu(x5: Tensor, w: Weights, p: str, act: bool = True) -> Tensor:
     """Conv2D 3x3 SAME on rank-5 [B,T,H,W,C] (weights shared over B,T; Q11)."""
     B, T, H, W, C = x5.shape
-    y = conv2d_nhwc(x5.reshape(B * T, H, W, C), w[p + "kernel"], w[p + "bias"], padding="same")
+    y = conv2d_nhwc(x5.reshape(B * T, H, W, C), w[p + "kernel"], w[p + "bias"], padding="same", store=False)
     if act:
-        y = elu(y)
+        y = _st(elu(y))  # the heads (act=False) leave as fp32 logits
     return y.reshape(B, T, H, W, -1)
 
 
@@ -422,7 +455,7 @@ def _conv3d_811(r5: Tensor, w: Weights, p: str) -> Tensor:
     k = w[p + "kernel"]  # [8,1,1,Ci,Co]
     x = r5.permute(0, 4, 1, 2, 3)  # [B,Ci,T,H,W]
     x = F.pad(x, (0, 0, 0, 0, 3, 4))
-    y = F.conv3d(x, k.permute(4, 3, 0, 1, 2), w[p + "bias"])
+    y = F.conv3d(x, _st(k).permute(4, 3, 0, 1, 2), w[p + "bias"])
     return elu(y.permute(0, 2, 3, 4, 1))
 
 
@@ -439,11 +472,11 @@ def decoder_forward(x: Tensor, res_list: List[Tensor], w: Weights, p: str = "dec
             r = res[ind_list[i]]
             r = r[:, None].expand(-1, 8, *r.shape[1:])  # tf.repeat 8x (:752)
             r = r.reshape(-1, 8, reshape_dim[i], reshape_dim[i], r.shape[-1])
-            x = x + _conv3d_811(r, w, f"{p}res_layer.{i}.")
+            x = _st(x + _conv3d_811(r, w, f"{p}res_layer.{i}."))
         if i == len(ind_list) - 1:
             fr = flow_res.reshape(-1, 64, 64, 96)
             fr = fr[:, None].expand(-1, 8, -1, -1, -1)
-            flow_x = x + _conv3d_811(fr, w, p + "res_f.")
+            flow_x = _st(x + _conv3d_811(fr, w, p + "res_f."))
     occ = _conv_elu(x, w, p + "output_layer.", act=False)
     for j in range(2):
         B, T, H, W, C = flow_x.shape

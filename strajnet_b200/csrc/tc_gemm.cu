@@ -438,6 +438,11 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
       p.BN = bn;
       if ((long long)p.m_tiles * (a.N / bn) * p.groups >= num_sms()) break;
     }
+    // tuning knob (tools/gemm_bn_sweep.py): force the n-tile width; read per call so that one process can sweep it
+    if (const char* e = getenv("SJ_TCG_BN")) {
+      const int bn = atoi(e);
+      if (bn >= 16 && bn <= 256 && bn % 16 == 0 && a.N % bn == 0) p.BN = bn;
+    }
   }
   p.n_tiles = a.N / p.BN;
   p.k_blocks = a.a_mode == 2 ? 4 * cdiv(a.mC, BK) : cdiv(a.K, BK);

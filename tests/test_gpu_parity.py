@@ -494,6 +494,20 @@ def test_strajnet_bf16_error_profile(sj, name, B, S, large):
     assert flat.max().item() < 0.08 * rng
     assert flat.mean().item() < 2.5e-2 and p999 < 0.1
     assert rms_b < 1.6 * rms_i + 1e-3
+    # The noise floor of bf16 storage itself: the same graph evaluated by the oracle with every kernel and every stored
+    # activation rounded to bf16 at layer granularity (O.bf16_storage) deviates from the fp32 oracle by as much as the CUDA
+    # path does -- the two bf16 evaluations are nearly uncorrelated (rounding noise through ~70 layers, not a systematic
+    # offset), so neither is a tighter reference for the other; what CAN be asserted is that the CUDA path is no noisier than
+    # an independent bf16 evaluation of the reference graph.  (Bit-level models exist per kernel: tests/test_gpu_kernels.py.)
+    with O.bf16_storage():
+        emu = O.forward_from_inputs(oracle_model(), O.CFG512 if large else CFG256, inp, large_ogm=large)
+    eflat = (emu - ref).abs().flatten()
+    e999 = eflat.kthvalue(int(0.999 * eflat.numel())).values.item()
+    rms_c, rms_e = flat.pow(2).mean().sqrt().item(), eflat.pow(2).mean().sqrt().item()
+    print(f"bf16 {name}: rms {rms_c:.3e} vs {rms_e:.3e} for the bf16-storage oracle (mean {eflat.mean().item():.3e}, p99.9 {e999:.3e}, "
+          f"max {eflat.max().item():.3e}); CUDA vs bf16-storage oracle rms {(y - emu).pow(2).mean().sqrt().item():.3e}")
+    assert rms_c < 1.3 * rms_e and flat.mean().item() < 1.3 * eflat.mean().item()
+    assert p999 < 1.3 * e999 and flat.max().item() < 1.5 * eflat.max().item()
 
 
 def test_inference_pipeline_stale_handle_raises(sj):

@@ -153,3 +153,23 @@ def test_large_input_mode_shapes():
     inp = O.make_inputs(1, 512, seed=1)
     res = O.encoder_forward(inp["ogm"], inp["map_img"], inp["flow"], w, O.CFG512, True)
     assert [tuple(r.shape) for r in res] == [(1, 4096, 96), (1, 4096, 96), (1, 1024, 192), (1, 256, 384)]
+
+
+def test_bf16_storage_mode_is_scoped_and_bf16_sized():
+    """O.bf16_storage(): layer-granularity model of the bf16 path's rounding points.  Outside the context the oracle is
+    untouched (bit-identical results before / after); inside, a Swin block deviates by bf16 rounding noise, not more."""
+    import torch
+    from oracle import strajnet_oracle as O
+    w = O.make_block_weights(96, 3, seed=3)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 16 * 16, 96, generator=g)
+    y0 = O.swin_block(x, w, "", 16, 16, 3, 8, 4)
+    with O.bf16_storage():
+        y1 = O.swin_block(x, w, "", 16, 16, 3, 8, 4)
+        assert O._EMULATE_BF16
+    assert not O._EMULATE_BF16
+    y2 = O.swin_block(x, w, "", 16, 16, 3, 8, 4)
+    assert torch.equal(y0, y2)
+    err = (y1 - y0).abs().max().item()
+    assert 1e-4 < err < 5e-2 * y0.abs().max().item()
+    assert torch.equal(y1, y1.to(torch.bfloat16).float())  # the block output is a stored tensor
