@@ -431,12 +431,17 @@ void tc_gemm(Ctx& c, const TcGemmP& a) {
   p.BN = pick_bn(a.N);
   p.m_tiles = cdiv(a.M, BM);
   if (!a.st_mean) {
-    // small problems are latency-bound: prefer the largest BN that still gives every SM a tile, else the narrowest
-    // (>= 32) so that the epilogue of each CTA is short
-    for (int bn = p.BN; bn >= 32; bn -= 16) {
+    // n-tile width: minimise  waves x (c0 + BN)  with waves = ceil(tiles / #SMs) and c0 = 160 columns' worth of per-tile
+    // fixed cost (A tile load, pipeline fill, epilogue drain).  Fitted to tools/gemm_bn_sweep.py on B200 (batch-16 shapes,
+    // M = 4096: N = 384 -> 96 (one wave of 128 tiles; the old "largest BN with >= #SMs tiles" rule took 64 = two waves, 6.9
+    // -> 5.7 us, 14.2 -> 9.8 us at K = 1536), N = 1152 -> 128 (9.8 -> 8.4 us), N = 1536 -> 192 (14.4 -> 11.8 us); M = 16384
+    // shapes keep their width).  Ties go to the wider tile.
+    long long best = -1;
+    for (int bn = 256; bn >= 32; bn -= 16) {
       if (a.N % bn) continue;
-      p.BN = bn;
-      if ((long long)p.m_tiles * (a.N / bn) * p.groups >= num_sms()) break;
+      const long long tiles = (long long)p.m_tiles * (a.N / bn) * p.groups;
+      const long long cost = ((tiles + num_sms() - 1) / num_sms()) * (160 + bn);
+      if (best < 0 || cost < best) { best = cost; p.BN = bn; }
     }
     // tuning knob (tools/gemm_bn_sweep.py): force the n-tile width; read per call so that one process can sweep it
     if (const char* e = getenv("SJ_TCG_BN")) {

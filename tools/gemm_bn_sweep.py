@@ -14,17 +14,24 @@ SHAPES = [  # (what, M, N, K, act)
 ]
 
 
-def time_layer(layer, x, n=60):
-    for _ in range(5):
+def time_layer(layer, x, n=40):
+    """us per launch with the launches replayed from a CUDA graph (eager calls are bound by ~13 us of Python each)"""
+    for _ in range(3):
         layer(x)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            layer(x)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        layer(x)
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
+    return e0.elapsed_time(e1) / (3 * n) * 1e3
 
 
 def main():
@@ -35,6 +42,7 @@ def main():
         layer.set_weights({"kernel": torch.randn(K, N, generator=g) * K ** -0.5, "bias": torch.randn(N, generator=g) * 0.1})
         x = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
         os.environ.pop("SJ_TCG_BN", None)
+        time_layer(layer, x)
         base = time_layer(layer, x)
         out = [f"{what:18s} M={M:5d} N={N:4d} K={K:4d}  heuristic {base:6.1f} us |"]
         for bn in range(256, 31, -16):
