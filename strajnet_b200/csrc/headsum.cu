@@ -6,113 +6,119 @@
 //
 // HBM-bound by construction: 2 x 36 B read per (waypoint, pixel), 4 B (fp32) or 1 B (quantised) written per output
 // element; no tensor cores (9 adds per output).  Work item = (sample, 8 x 32 pixel tile); its 16 (waypoint, head) halo
-// tiles stream through a 4-stage cp.async ring (rows are contiguous 18-channel fp16 pixels, copied as 16-byte pieces
-// with zero fill outside the image); each thread owns one pixel, reads its nine fp16 pairs per sub-item conflict-free
-// (pixel stride 9 words) and finally writes its 32 output channels as one 128-byte line.
+// tiles stream through a 4-stage ring filled by TMA: one thread issues two 3-D box loads per stage (the image rows are
+// viewed as 2304 32-bit words = 256 pixels x 9 fp16 pairs; a 34-pixel halo row is 306 words, more than one box dimension
+// may hold, so it arrives as two overlapping 184-word boxes whose starts are 16-byte aligned), out-of-image rows / columns
+// are zero-filled by the TMA unit (= the SAME padding of the 3x3 convolution).  Each thread owns one pixel, reads its nine
+// fp16 pairs per sub-item conflict-free (pixel stride 9 words; the second box starts 128 words into the row and 7424 bytes
+// into the stage, which keeps the two halves of a warp on disjoint banks) and finally writes its 32 output channels as one 128-byte line.
+// (The first version filled the ring with per-thread 16-byte cp.async: address selects and border predicates were ~55 %
+// of the instructions of an instruction-bound kernel -- issue slots 58 % busy at 0.66 of the HBM peak.)
 #include <cuda_fp16.h>
 
+#include <cstdio>
+
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace sj {
 namespace {
 
+using namespace tc;
+
 constexpr int TW = 32, TH = 8, NTHREADS = TW * TH;
-constexpr int ZCH = 18, PIX_B = ZCH * 2;               // 36 bytes per pixel
-constexpr int ROW_B = 256 * PIX_B;                     // 9216 bytes per image row
-constexpr int LEAD = 12;                               // the halo pixel x0-1 starts 12 bytes into the 16-byte aligned copy
-constexpr int ROW_CHUNKS = ((TW + 2) * PIX_B + LEAD + 15) / 16;  // 78
-constexpr int SROW = ROW_CHUNKS * 16;                  // 1248 bytes per staged row
-constexpr int STAGE = (TH + 2) * SROW;                 // 12480
+constexpr int PIX_W = 9;                               // 32-bit words per pixel (18 fp16 columns)
+constexpr int ROW_W = 256 * PIX_W;                     // 2304 words per image row
+constexpr int LEAD_W = 3;                              // the box starts 3 words before the halo pixel x0-1: 16-byte aligned
+constexpr int BOX_W = 184;                             // words per box row (A: words [0,184) from there, B: [128,312))
+constexpr int B_WORD0 = 128;                           // first word of box B (a multiple of 32: both halves of a warp on the same bank map)
+constexpr int SPLIT_TX = 17;                           // pixels tx < 17 read box A (needs words < 3 + 9*16 + 27 = 174)
+constexpr int SROW = BOX_W * 4;                        // 736 bytes per staged row
+constexpr int SUB_A = 0, SUB_B = 7424;                 // box offsets inside a stage (128-byte aligned)
+constexpr int STAGE = 14848;                           // 7424 + 7360, rounded up to 128
 constexpr int NST = 4;
 static_assert(16 % NST == 0, "stage index must follow the sub-item index");
+static_assert(SUB_B % 128 == 0 && STAGE % 128 == 0 && SUB_B >= (TH + 2) * SROW && STAGE >= SUB_B + (TH + 2) * SROW, "stage layout");
+static_assert(LEAD_W + PIX_W * (SPLIT_TX - 1) + 3 * PIX_W <= BOX_W && LEAD_W + PIX_W * SPLIT_TX >= B_WORD0 &&
+              LEAD_W + PIX_W * (TW - 1) + 3 * PIX_W <= B_WORD0 + BOX_W && (TW * PIX_W) % 4 == 0 && (PIX_W + LEAD_W) % 4 == 0 &&
+              B_WORD0 % 32 == 0 && BOX_W % 4 == 0, "box coverage, 16-byte aligned box starts");
 constexpr int TILES_X = 256 / TW, TILES_PER_IMG = TILES_X * (256 / TH);
 
 struct HeadSumP {
-  const uint8_t* z[2];  // fp16 [B*8,256,256,18]: occupancy head, flow head
   const float* bias;    // [2][2]
   void* out;
   int num_items, out_layout;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
-__global__ void __launch_bounds__(NTHREADS, 4) head_tapsum_kernel(const HeadSumP p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(NTHREADS, 3)
+head_tapsum_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapF, const HeadSumP p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full[NST];
   const int tid = threadIdx.x, ty = tid / TW, tx = tid % TW;
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const int n_my = p.num_items > (int)blockIdx.x ? (p.num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total = n_my * 16;
+  if (tid == 0) {
+    prefetch_tmap(&mapO);
+    prefetch_tmap(&mapF);
+    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   pdl_wait();
   pdl_trigger();
 
-  // Loader: the 16-byte pieces of a halo tile are dealt to the threads once (piece tid + 256 k -> row, column), so that a
-  // sub-item costs each thread four address adds and four cp.async; validity (image border) changes only with the item.
-  constexpr int NPIECE = (TH + 2) * ROW_CHUNKS, KMAX = (NPIECE + NTHREADS - 1) / NTHREADS;
-  int p_soff[KMAX], p_row[KMAX], p_col[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const int c = tid + k * NTHREADS;
-    p_row[k] = c < NPIECE ? c / ROW_CHUNKS : -100000;  // never valid
-    p_col[k] = (c % ROW_CHUNKS) * 16;
-    p_soff[k] = (c / ROW_CHUNKS) * SROW + p_col[k];
-  }
-  int l_item = -1;
-  int l_goff[KMAX];  // byte offset inside one [256,256,18] image
-  unsigned l_ok = 0;
-  long long l_img0 = 0;
-  auto load = [&](int s) {
-    if (s < total) {
-      const int item = blockIdx.x + (s >> 4) * gridDim.x, th = s & 15;
-      if (item != l_item) {  // new tile: origin, validity of this thread's pieces
-        l_item = item;
-        const int b = item / TILES_PER_IMG, tr = item % TILES_PER_IMG;
-        const int y0 = (tr / TILES_X) * TH, x0 = (tr % TILES_X) * TW;
-        const int col0 = x0 * PIX_B - PIX_B - LEAD;  // 16-byte aligned (x0 is a multiple of 32)
-        l_img0 = (long long)b * 8 * 256 * ROW_B;
-        l_ok = 0;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int y = y0 - 1 + p_row[k], off = col0 + p_col[k];
-          const bool ok = y >= 0 && y < 256 && off >= 0 && off < ROW_B;
-          l_ok |= (ok ? 1u : 0u) << k;
-          l_goff[k] = y * ROW_B + off;
-        }
-      }
-      const uint8_t* img = p.z[th & 1] + l_img0 + (long long)(th >> 1) * 256 * ROW_B;
-      const uint32_t dst0 = smem_base + (s % NST) * STAGE;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (p_row[k] >= 0) {
-          const bool ok = (l_ok >> k) & 1;
-          cp_async16(dst0 + p_soff[k], ok ? img + l_goff[k] : p.z[0], ok ? 16 : 0);
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+  // sub-item s = 16 * (local item) + 2 * waypoint + head; executed by thread 0 only.  A macro, not a lambda: the descriptor
+  // operand of the TMA instruction must be the kernel parameter itself (an out-of-line closure holding references to the
+  // maps faulted with "illegal instruction").
+#define SJ_TAP_LOAD(S)                                                                                  \
+  do {                                                                                                  \
+    const int s_ = (S);                                                                                 \
+    if (s_ < total) {                                                                                   \
+      const int item_ = blockIdx.x + (s_ >> 4) * gridDim.x, th_ = s_ & 15;                              \
+      const int b_ = item_ / TILES_PER_IMG, tr_ = item_ % TILES_PER_IMG;                                \
+      const int c0_ = ((tr_ % TILES_X) * TW - 1) * PIX_W - LEAD_W, c1_ = (tr_ / TILES_X) * TH - 1, c2_ = b_ * 8 + (th_ >> 1); \
+      uint8_t* dst_ = smem + (s_ % NST) * STAGE;                                                        \
+      mbar_expect_tx(&full[s_ % NST], 2 * (TH + 2) * SROW);                                             \
+      if (th_ & 1) {                                                                                    \
+        tma_load_3d(dst_ + SUB_A, &mapF, &full[s_ % NST], c0_, c1_, c2_);                               \
+        tma_load_3d(dst_ + SUB_B, &mapF, &full[s_ % NST], c0_ + B_WORD0, c1_, c2_);                     \
+      } else {                                                                                          \
+        tma_load_3d(dst_ + SUB_A, &mapO, &full[s_ % NST], c0_, c1_, c2_);                               \
+        tma_load_3d(dst_ + SUB_B, &mapO, &full[s_ % NST], c0_ + B_WORD0, c1_, c2_);                     \
+      }                                                                                                 \
+    }                                                                                                   \
+  } while (0)
+  if (tid == 0)
+    for (int s0 = 0; s0 < NST; ++s0) SJ_TAP_LOAD(s0);
 
-  for (int s = 0; s < NST - 1; ++s) load(s);
   const float b00 = p.bias[0], b01 = p.bias[1], b10 = p.bias[2], b11 = p.bias[3];
+  // this thread's pixel (ty, tx) inside a stage: halo-row word 9 * tx, in box A or box B
+  const int my_off = (tx < SPLIT_TX ? SUB_A + (LEAD_W + tx * PIX_W) * 4 : SUB_B + (LEAD_W + tx * PIX_W - B_WORD0) * 4) + ty * SROW;
   int s = 0;
   for (int it = 0; it < n_my; ++it) {
     float v[32];
 #pragma unroll
     for (int th = 0; th < 16; ++th, ++s) {  // s % NST == th % NST (16 is a multiple of NST): stage offsets are constants
-      asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
-      __syncthreads();
-      load(s + NST - 1);  // refills the stage every thread finished reading before the barrier above
-      const uint8_t* st = smem + (th % NST) * STAGE + LEAD;
+      mbar_wait(&full[th % NST], (uint32_t)(s / NST) & 1);
+      const uint8_t* st = smem + (th % NST) * STAGE + my_off;
       float a0 = (th & 1) ? b10 : b00, a1 = (th & 1) ? b11 : b01;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const __half2 h = *reinterpret_cast<const __half2*>(st + (ty + tap / 3) * SROW + (tx + tap % 3) * PIX_B + tap * 4);
+        const __half2 h = *reinterpret_cast<const __half2*>(st + (tap / 3) * SROW + (tap % 3) * PIX_W * 4 + tap * 4);
         const float2 f = __half22float2(h);
         a0 += f.x;
         a1 += f.y;
       }
       v[2 * th] = a0;
       v[2 * th + 1] = a1;
+      // Stage hand-back: the generic-proxy reads above are ordered before the async-proxy (TMA) write that reuses the
+      // stage by a proxy fence + the block barrier, and the stage refilled here is the one read in the PREVIOUS sub-item
+      // (three loads in flight, one sub-item of slack).  The first version refilled the stage just read, without the fence:
+      // bit-exact in isolation, but whole-model runs showed rare corrupted pixel groups at batch 16.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0 && s >= 1) SJ_TAP_LOAD(s - 1 + NST);
     }
     const int item = blockIdx.x + it * gridDim.x;
     const int b = item / TILES_PER_IMG, tr = item % TILES_PER_IMG;
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 4) head_tapsum_kernel(const HeadSumP
             make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef SJ_TAP_LOAD
 }
 
 }  // namespace
@@ -145,12 +151,21 @@ __global__ void __launch_bounds__(NTHREADS, 4) head_tapsum_kernel(const HeadSumP
 void head_tapsum(Ctx& c, const void* z_occ, const void* z_flow, const float* bias, int B, int out_layout, void* out) {
   if (!c.ok() || c.dry) return;
   HeadSumP p{};
-  p.z[0] = (const uint8_t*)z_occ; p.z[1] = (const uint8_t*)z_flow; p.bias = bias; p.out = out;
+  p.bias = bias; p.out = out;
   p.num_items = B * TILES_PER_IMG; p.out_layout = out_layout;
-  const size_t smem = NST * STAGE;
-  if (!SJ_SMEM_LIMIT_OK(head_tapsum_kernel, (int)(NST * STAGE))) { c.fail(SJ_ECUDA); return; }
-  const int grid = p.num_items < 4 * num_sms() ? p.num_items : 4 * num_sms();
-  SJ_LAUNCH(c, "head_tapsum", head_tapsum_kernel, grid, NTHREADS, smem, p);
+  CUtensorMap mapO, mapF;
+  uint64_t dz[3] = {(uint64_t)ROW_W, 256, (uint64_t)B * 8};
+  uint64_t sz[2] = {(uint64_t)ROW_W * 4, (uint64_t)256 * ROW_W * 4};
+  uint32_t bz[3] = {BOX_W, TH + 2, 1};
+  if (!encode_tmap(&mapO, z_occ, 3, dz, sz, bz, 0, 4) || !encode_tmap(&mapF, z_flow, 3, dz, sz, bz, 0, 4)) {
+    snprintf(tls().cuda_err, sizeof(tls().cuda_err), "cuTensorMapEncodeTiled failed (head_tapsum)");
+    c.fail(SJ_ECUDA);
+    return;
+  }
+  const size_t smem = NST * STAGE + 128;
+  if (!SJ_SMEM_LIMIT_OK(head_tapsum_kernel, (int)(NST * STAGE + 128))) { c.fail(SJ_ECUDA); return; }
+  const int grid = p.num_items < 3 * num_sms() ? p.num_items : 3 * num_sms();
+  SJ_LAUNCH(c, "head_tapsum", head_tapsum_kernel, grid, NTHREADS, smem, mapO, mapF, p);
 }
 
 }  // namespace sj

@@ -253,8 +253,8 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
 }  // namespace tc
 
 // ---- host: tensor-map encoding -------------------------------------------------------------------
-// dims/strides innermost first; strides in bytes for dims 1..rank-1; bf16 elements
+// dims/strides innermost first; strides in bytes for dims 1..rank-1; bf16 elements (elem_bytes = 4: 32-bit words)
 bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box, int swizzle_bytes);
+                 const uint32_t* box, int swizzle_bytes, int elem_bytes = 2);
 
 }  // namespace sj

@@ -536,3 +536,16 @@ def test_vehicle_plane_only_input_is_bit_identical(sj):
         y1 = m(plane, inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
         y2 = m((plane != 0).to(torch.uint8), inp["map_img"], training=False, obs=inp["obs"], occ=inp["occ"], flow=inp["flow"])
         assert torch.equal(y, y1) and torch.equal(y, y2)
+
+
+def test_bf16_forward_is_run_to_run_deterministic(sj):
+    """No kernel of the bf16 path uses atomics or order-dependent reductions, so repeated forwards must agree bit for bit,
+    also when the batch size changes in between (new workspace, new tensor maps, different tiles per CTA).  This is the
+    guard for hand-off races in the TMA / mbarrier pipelines: the first TMA-fed version of head_tapsum_kernel passed every
+    parity gate in isolation and corrupted a few hundred logits per batch-16 forward in this sequence."""
+    m = _model(sj, dtype="bfloat16")
+    for B in (1, 2, 16, 1, 16):
+        inp = O.make_inputs(B, 256, seed=31)
+        y0 = _fwd(m, inp).clone()
+        for _ in range(3):
+            assert torch.equal(_fwd(m, inp), y0), f"batch {B}: two forwards of the same inputs differ"
