@@ -13,5 +13,5 @@ STEPS=10 timeout 300 python tools/role_times.py > gpurun_out/final_roles.txt 2>&
 N=$(python tools/one_step.py 2>/dev/null | grep -o "[0-9]*$")
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches.csv python tools/one_step.py > /dev/null 2>&1
 python tools/last_step.py gpurun_out/final_launches.csv $N > gpurun_out/final_launches_one_step.txt; tail -25 gpurun_out/final_launches_one_step.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tc_patch_embed|tc_wmsa|fg_offset_mma" -s 14 -c 7 -f -o gpurun_out/final_new_kernels python tools/one_step.py > gpurun_out/final_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tc_patch_embed|tc_wmsa|fg_offset_mma|head_tapsum" -s 16 -c 8 -f -o gpurun_out/final_new_kernels python tools/one_step.py > gpurun_out/final_ncu.log 2>&1
 ls -la gpurun_out/final_new_kernels.ncu-rep
