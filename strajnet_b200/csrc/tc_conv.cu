@@ -19,6 +19,7 @@
 //   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue (bias + ELU + bf16,
 //     16-byte stores); accumulators double-buffered in TMEM when 4*Cout fits 512 columns.
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -69,7 +70,7 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr int AROWB = AKC * 2;
   constexpr int ANCH = (NCH * KC + AKC - 1) / AKC;  // activation chunks per slot
   const int b_sub = p.Cout * ROWB;            // one weight tile: Cout rows x one chunk
-  const int b_stage = 2 * NCH * b_sub;        // streaming: up to two phases per tap
+  const int b_stage = NCH * b_sub;            // streaming: one (tap, column phase) weight tile per stage
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.na * p.a_slot;
   const int b_bytes = RESB ? 8 * NCH * b_sub : p.nbs * b_stage;
@@ -149,17 +150,17 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               for (int di = 0; di < 3; ++di) {
                 const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);  // centre column tap first (see the MMA warp)
                 const int dx = dxi - 1, nb = dx == 0 ? 2 : 1;
-                mbar_wait(&bempty[bs_], bph ^ 1);
-                mbar_expect_tx(&bfull[bs_], nb * NCH * b_sub);
-                for (int s = 0; s < nb; ++s) {
+                for (int s = 0; s < nb; ++s) {  // the centre column tap feeds both column phases: two stages
                   const int px = dx < 0 ? 0 : (dx > 0 ? 1 : s);
                   const int b = dx - px + 1;  // column tap inside phase px: low-res offset = b - 1 + px
+                  mbar_wait(&bempty[bs_], bph ^ 1);
+                  mbar_expect_tx(&bfull[bs_], NCH * b_sub);
 #pragma unroll
                   for (int ch = 0; ch < NCH; ++ch)
-                    tma_load_2d(smem_b + bs_ * b_stage + (s * NCH + ch) * b_sub, &mapB, &bfull[bs_],
+                    tma_load_2d(smem_b + bs_ * b_stage + ch * b_sub, &mapB, &bfull[bs_],
                                 (a * 2 + b) * p.Cin + (cg * NCH + ch) * KC, (py * 2 + px) * p.Cout);
+                  if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
                 }
-                if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
               }
           }
         }
@@ -196,39 +197,45 @@ tc_upconv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int di = 0; di < 3; ++di) {
               const int dxi = di == 0 ? 1 : (di == 1 ? 0 : 2);  // same stage order as the producer
-              uint32_t bstage_lo = 0;
-              if (!RESB) {
-                mbar_wait(&bfull[bs_], bph);
-                tc_fence_after();
-                bstage_lo = b_base_lo + (uint32_t)bs_ * 2 * NCH * b_sub16;
-              }
-              // column tap dx = dxi-1 feeds phase px iff b = dxi - px is 0 or 1; in a streamed stage the tile of px1 is
-              // slot 1 only for the shared centre tap
+              // column tap dx = dxi-1 feeds phase px iff b = dxi - px is 0 or 1.  Streamed weights: one stage per
+              // (tap, column phase) tile -- the centre tap is two stages (px 0 then px 1), the others one; both MMA warps
+              // walk every stage and release it, only the warp whose phase the tile belongs to issues MMAs
               const int b = dxi - px;
-              if (elect_one()) {
-                if (b == 0 || b == 1) {
-                  const int sl = (dxi == 1 && px == 1) ? 1 : 0;
+              const int nst = RESB ? 1 : (dxi == 1 ? 2 : 1);
 #pragma unroll
-                  for (int ch = 0; ch < NCH; ++ch) {
-                    // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
-                    const uint32_t view = a_lo + (((a * PW + dxi) * AROWB) >> 4);
-                    const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
-                                             : bstage_lo + (uint32_t)(sl * NCH + ch) * b_sub16;
+              for (int st = 0; st < nst; ++st) {
+                uint32_t bstage_lo = 0;
+                if (!RESB) {
+                  mbar_wait(&bfull[bs_], bph);
+                  tc_fence_after();
+                  bstage_lo = b_base_lo + (uint32_t)bs_ * NCH * b_sub16;
+                }
+                const int tile_px = dxi == 0 ? 0 : (dxi == 2 ? 1 : st);  // whose tile this stage holds
+                const bool mine = (b == 0 || b == 1) && (RESB || tile_px == px);
+                if (elect_one()) {
+                  if (mine) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                      const int kk = ch * (KC / 16) + k;  // K step (16 channels) within the slot
-                      const uint32_t va = view + (kk / (AKC / 16)) * A_SUB16 + 2 * (kk % (AKC / 16));
-                      umma_bf16_w(d_tmem, va, A_HI, vb + 2 * k, B_HI, idesc, started);
-                      started = 1;
+                    for (int ch = 0; ch < NCH; ++ch) {
+                      // shifted view of the staged patch: MMA row 8*ty+tx -> patch pixel (ty + a, tx + dxi)
+                      const uint32_t view = a_lo + (((a * PW + dxi) * AROWB) >> 4);
+                      const uint32_t vb = RESB ? b_base_lo + (uint32_t)(((a * NCH + ch) * 4) + px * 2 + b) * b_sub16
+                                               : bstage_lo + (uint32_t)ch * b_sub16;
+#pragma unroll
+                      for (int k = 0; k < KC / 16; ++k) {
+                        const int kk = ch * (KC / 16) + k;  // K step (16 channels) within the slot
+                        const uint32_t va = view + (kk / (AKC / 16)) * A_SUB16 + 2 * (kk % (AKC / 16));
+                        umma_bf16_w(d_tmem, va, A_HI, vb + 2 * k, B_HI, idesc, started);
+                        started = 1;
+                      }
                     }
                   }
+                  if (!RESB) umma_commit(&bempty[bs_]);
                 }
-                if (!RESB) umma_commit(&bempty[bs_]);
-              }
-              __syncwarp();
-              if (b == 0 || b == 1) started = 1;
-              if (!RESB) {
-                if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
+                __syncwarp();
+                if (mine) started = 1;
+                if (!RESB) {
+                  if (++bs_ == p.nbs) { bs_ = 0; bph ^= 1; }
+                }
               }
             }
           }
@@ -336,7 +343,11 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
   }
   p.a_sub = (PH * PW * AKC * 2 + 1023) & ~1023;
   p.a_slot = ANCH * p.a_sub;
-  p.na = 3;
+  // Streamed weights: the MMA warps were waiting on the weight ring (ncu: tensor pipe 48 % at 384 -> 192 with long-scoreboard
+  // stalls, L2 throughput 18 %: ring depth, not bandwidth).  Two patch slots instead of three (a patch lasts eight weight
+  // stages, longer than its own TMA round trip) and ONE (tap, column phase) tile per stage instead of a two-tile stage that
+  // four of six taps half filled: 2 -> 6 stages at Cout = 192, 4 -> 8 at Cout = 128; 92 -> 70 us and 90 -> 72 us per launch.
+  p.na = RESB ? 3 : 2;
   const int b_sub = p.Cout * rowb;
   const int budget = 222 * 1024 - 1024 - 2048 - 16384;  // alignment slack + barriers + bias + output staging
   int b_bytes;
@@ -344,7 +355,7 @@ void launch_upconv(Ctx& c, const void* x, const void* w_tc, ConvP p) {
     b_bytes = 8 * NCH * b_sub;
     p.nbs = 1;
   } else {
-    const int b_stage = 2 * NCH * b_sub;
+    const int b_stage = NCH * b_sub;  // one (tap, column phase) tile per stage
     p.nbs = (budget - p.na * p.a_slot) / b_stage;
     if (p.nbs > MAX_STAGES) p.nbs = MAX_STAGES;
     if (p.nbs < 2) { c.fail(SJ_EUNSUPPORTED); return; }
