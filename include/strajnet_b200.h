@@ -31,7 +31,7 @@
  *     SJ_DISABLE_FUSED_STATS, SJ_DISABLE_FUSED_MLP, SJ_DISABLE_UPCONV4, SJ_DISABLE_UPCONV1P, SJ_DISABLE_HEAD_FUSION, SJ_DISABLE_RESADD2, SJ_DISABLE_LOCKSTEP,
  *     SJ_DISABLE_ATTN_MMA, SJ_DISABLE_IM2COL_STAGED, SJ_DISABLE_NORM_FAST, SJ_DISABLE_FG_OFFSET_MMA (fall back to the
  *     previous kernel), SJ_NO_SIDE_STREAM (keep the trajectory actor branch on the caller's stream), SJ_TCG_EW=16 / SJ_TCG_RPF (tc_gemm epilogue
- *     variants), SJ_NO_PDL (forces the PDL mask to 0).
+ *     variants), SJ_TCG_BN=<n> (forces the tc_gemm n-tile width; read per call: tools/gemm_bn_sweep.py), SJ_NO_PDL (forces the PDL mask to 0).
  */
 #ifndef STRAJNET_B200_H_
 #define STRAJNET_B200_H_
