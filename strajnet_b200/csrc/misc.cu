@@ -459,37 +459,50 @@ __device__ __forceinline__ void st8_bf16(bf16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// bf16 form: 8 channels (one 16-byte store) per thread, 32-bit index arithmetic (the generic kernel above spends most of
-// its 16 us on two 64-bit divisions and 8-byte stores for a 25 MB output)
+// bf16 form: a thread owns 8 channels of one (sample, token) and writes them for all 8 waypoints -- the encoder feature and
+// the projection weights of those channels are loaded once instead of eight times (the generic kernel above: one element
+// group per thread, five dependent loads each, 16 us for a 25 MB output)
 __global__ void __launch_bounds__(256) build_query_bf16_kernel(const bf16* __restrict__ q2, const float* __restrict__ off,
                                                                const float* __restrict__ w2, const float* __restrict__ b2,
                                                                int B, int fg, bf16* __restrict__ query) {
   pdl_wait();
   pdl_trigger();
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;  // over B*8*256 rows x 48 groups of 8 channels
-  if (i >= (uint32_t)B * 2048u * 48u) return;
-  const uint32_t row = i / 48u, c = (i - row * 48u) * 8u;  // row = (b*8 + t)*256 + l
-  const uint32_t l = row & 255u, b = row >> 11;
-  float v[8];
-  if (q2) ld8_bf16(q2 + ((size_t)b * 256 + l) * 384 + c, v);
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;  // over B*256 tokens x 48 groups of 8 channels
+  if (i >= (uint32_t)B * 256u * 48u) return;
+  const uint32_t tok = i / 48u, c = (i - tok * 48u) * 8u;  // tok = b*256 + l
+  const uint32_t b = tok >> 8, l = tok & 255u;
+  float base[8], w0[8], w1[8];
+  if (q2) ld8_bf16(q2 + (size_t)tok * 384 + c, base);
   else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int j = 0; j < 8; ++j) base[j] = 0.f;
   }
   if (fg) {
-    const float2 o = *reinterpret_cast<const float2*>(off + (size_t)row * 2);
 #pragma unroll
     for (int j = 0; j < 8; j += 4) {
-      const float4 w0 = *reinterpret_cast<const float4*>(w2 + c + j), w1 = *reinterpret_cast<const float4*>(w2 + 384 + c + j);
-      const float4 bb = *reinterpret_cast<const float4*>(b2 + c + j);
-      // flow_hidden = off . Wp2 + bp2 is formed first, then added to the query (modules.py:830-831)
-      v[j] += fmaf(o.y, w1.x, o.x * w0.x) + bb.x;
-      v[j + 1] += fmaf(o.y, w1.y, o.x * w0.y) + bb.y;
-      v[j + 2] += fmaf(o.y, w1.z, o.x * w0.z) + bb.z;
-      v[j + 3] += fmaf(o.y, w1.w, o.x * w0.w) + bb.w;
+      const float4 a = *reinterpret_cast<const float4*>(w2 + c + j), d = *reinterpret_cast<const float4*>(w2 + 384 + c + j);
+      w0[j] = a.x; w0[j + 1] = a.y; w0[j + 2] = a.z; w0[j + 3] = a.w;
+      w1[j] = d.x; w1[j + 1] = d.y; w1[j + 2] = d.z; w1[j + 3] = d.w;
     }
   }
-  st8_bf16(query + (size_t)row * 384 + c, v);
+  float bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bb[j] = fg ? b2[c + j] : 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const size_t row = ((size_t)b * 8 + t) * 256 + l;
+    float v[8];
+    if (fg) {
+      const float2 o = *reinterpret_cast<const float2*>(off + row * 2);
+      // flow_hidden = off . Wp2 + bp2 is formed first, then added to the query (modules.py:830-831)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = base[j] + (fmaf(o.y, w1[j], o.x * w0[j]) + bb[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = base[j];
+    }
+    st8_bf16(query + row * 384 + c, v);
+  }
 }
 
 // ---------------------------------------------------------------- trajectory glue
@@ -777,7 +790,7 @@ void build_query(Ctx& c, const void* q2, const float* off, const SjFgmsaW* w, in
   const float* w2 = fg ? w->offproj2_w : nullptr;
   const float* b2 = fg ? w->offproj2_b : nullptr;
   if (fg && (!w2 || !b2 || !off)) { c.fail(SJ_EINVAL); return; }
-  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "build_query", build_query_bf16_kernel, cdiv(n / 2, 256), 256, 0, (const bf16*)q2, off, w2, b2, B, fg, (bf16*)query);
+  if (c.dtype == SJ_BF16) SJ_LAUNCH(c, "build_query", build_query_bf16_kernel, cdiv(n / 16, 256), 256, 0, (const bf16*)q2, off, w2, b2, B, fg, (bf16*)query);
   else SJ_LAUNCH(c, "build_query", build_query_kernel<float>, cdiv(n, 256), 256, 0, (const float*)q2, off, w2, b2, B, fg, (float*)query);
 }
 void fg_flow_hidden(Ctx& c, const float* off, const SjFgmsaW* w, int B, void* out) {
