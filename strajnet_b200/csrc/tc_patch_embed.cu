@@ -3,13 +3,13 @@
 // (PatchEmbed.call modules.py:437-446, the vec + map sum and all_patch_norm :580-587 / :602, patch_embed_flow + flow_norm
 // :576-577), plus the LayerNorm statistics of y for norm1 of the first Swin block.
 //
-// As im2col -> tcgen05 GEMM -> combine this stage was 8 launches and 145 us of the batch-16 step for 0.3 GFLOP: the
+// As im2col -> tcgen05 GEMM -> combine this stage was 8 launches and 168 us of the batch-16 step (80 us now) for 0.3 GFLOP: the
 // im2col matrix (25 MB for the occupancy raster) and the conv outputs made a round trip through HBM each.  Here one CTA
 // turns 128 consecutive tokens into finished tokens:
-//   * all 8 warps read the tile's image rows with coalesced 4-byte loads (the 4 x Cin x es source elements of a token
-//     and a kernel row are contiguous, and so are the tokens of a token row), convert to bf16 and scatter them into the
-//     K-major SWIZZLE_128B A tile(s) in shared memory ("im2col in shared memory"; element stride es = 2 picks plane 0 of
-//     the [.., 11, 2] raster);
+//   * all 8 warps read the tile's image rows with coalesced 16-byte loads (the 4 x Cin x es source elements of a token
+//     and a kernel row are contiguous, and so are the tokens of a token row; a thread keeps one unit of all 8 (token row,
+//     kernel row) segments in flight), convert to bf16 and scatter them into the K-major SWIZZLE_128B A tile(s) in shared
+//     memory ("im2col in shared memory"; element stride es = 2 picks plane 0 of the [.., 11, 2] raster);
 //   * one elected lane issues the K = 16*Cin (zero-padded to 64) MMAs against the resident projection weights
 //     (36 KB + 12 KB), one TMEM accumulator per input;
 //   * the accumulators are staged through shared memory (over the dead A tile) so that a warp owns a token: bias, the
